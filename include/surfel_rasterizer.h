@@ -1,0 +1,132 @@
+/* surfel_rasterizer.h -- C ABI of the B200-native 2D-Gaussian-surfel rasterizer.
+ *
+ * Drop-in boundary for LaRa's third_party/diff-surfel-rasterization ("DSR").  The
+ * reference crosses Python -> native at three pybind entry points
+ * (DSR/ext.cpp:15-19, DSR/rasterize_points.h:18-68):
+ *
+ *     rasterize_gaussians            -> srf_forward_preprocess + srf_forward_render
+ *     rasterize_gaussians_backward   -> srf_backward
+ *     mark_visible                   -> srf_mark_visible
+ *
+ * which in turn call CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+ * (DSR/cuda_rasterizer/rasterizer.h:24-86) with raw pointers.  This header is the
+ * raw-pointer level: plain C, device pointers + sizes + a cudaStream_t, int status
+ * return (0 = ok; otherwise srf_last_error() describes the failure).  No torch
+ * types, no allocation inside the library: the caller owns every buffer (the
+ * reference's three growable byte blobs become caller-allocated workspaces whose
+ * sizes the srf_*_bytes functions report).  All entry points only enqueue work on
+ * `stream`; none of them synchronises.
+ *
+ * Pointer conventions: every pointer is a CUDA device pointer unless it says "host".
+ * Workspaces must be 256-byte aligned.  Matrices follow the reference:
+ * `viewmatrix` / `projmatrix` are 16 floats, column-major (i.e. the row-major
+ * memory of LaRa's world_view_transform = w2c^T, lightning/utils.py:33-48).
+ */
+#ifndef SURFEL_RASTERIZER_H_
+#define SURFEL_RASTERIZER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRF_ABI_VERSION 1
+
+/* cudaStream_t without pulling in cuda_runtime.h */
+typedef void* srf_stream_t;
+
+/* Library / ABI identification. */
+int srf_abi_version(void);
+/* Thread-local description of the last failure (never NULL). */
+const char* srf_last_error(void);
+
+/* ---- workspace sizing (host-only, no CUDA calls) --------------------------------
+ * Replaces the reference's required<GeometryState/ImageState/BinningState>(n)
+ * (DSR/cuda_rasterizer/rasterizer_impl.h:64-70, rasterizer_impl.cu:155-194).
+ *   geom  : per-Gaussian state  (GeomRecord[P], depths[P], rects[P])
+ *   tile  : per-tile state      (counts, counters, ranges, cursors, big-tile list)
+ *   image : per-pixel state     (final_T/dist1/dist2 planes, n_contrib/median planes)
+ *   entries / point_list : per-instance scratch and the sorted per-tile index list,
+ *                          sized by an instance *capacity* chosen by the caller.
+ */
+int srf_geom_state_bytes(int P, size_t* bytes);
+int srf_tile_state_bytes(int H, int W, size_t* bytes);
+int srf_image_state_bytes(int H, int W, size_t* bytes);
+int srf_binning_bytes(size_t capacity, size_t* entries_bytes, size_t* point_list_bytes);
+/* scratch needed by srf_backward: one 80-byte gradient accumulation record per Gaussian */
+int srf_backward_scratch_bytes(int P, size_t* bytes);
+
+/* Byte offsets of the sub-arrays inside the workspaces (for tests / tooling that
+ * inspect state the way the reference's blobs can be parsed).
+ *   geom_off[3]  : rec, depths, rects
+ *   tile_off[5]  : tile_count, counters(4 x u32: num_rendered, n_big, -, -), ranges(uint2), cursor, big_list
+ *   image_off[2] : accum(3 float planes), n_contrib(2 u32 planes)                    */
+int srf_state_layout(int P, int H, int W, size_t geom_off[3], size_t tile_off[5], size_t image_off[2]);
+
+/* ---- forward, stage 1: per-Gaussian preprocess + per-tile counting + tile scan ----
+ * Replaces FORWARD::preprocess, cub::DeviceScan::InclusiveSum and the blocking
+ * cudaMemcpy of num_rendered (rasterizer_impl.cu:241-282).  Writes radii[P] and the
+ * geom/tile workspaces; copies num_rendered (uint32) asynchronously to
+ * `num_rendered_host` (pinned host memory, may be NULL) -- wait on the stream or an
+ * event to read it.  `shs` XOR `colors_precomp`, (`scales`,`rotations`) XOR
+ * `transMat_precomp` as in the reference (NULL = not given).  scale_modifier and
+ * projmatrix are accepted for signature parity and ignored, exactly like the
+ * reference (forward.cu:95; auxiliary.h:173-184 only uses the view matrix). */
+int srf_forward_preprocess(srf_stream_t stream, int P, int D, int M,
+                           const float* means3D, const float* shs, const float* colors_precomp,
+                           const float* opacities, const float* scales, float scale_modifier,
+                           const float* rotations, const float* transMat_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* campos,
+                           float tan_fovx, float tan_fovy, int image_height, int image_width,
+                           int prefiltered,
+                           int* radii, void* geom_state, void* tile_state,
+                           uint32_t* num_rendered_host);
+
+/* ---- forward, stage 2: tile-bucket scatter, per-tile depth sort, blend ------------
+ * Replaces duplicateWithKeys, cub::DeviceRadixSort::SortPairs, identifyTileRanges and
+ * FORWARD::render (rasterizer_impl.cu:290-341).  `capacity` is the number of
+ * instances `entries` / `point_list` can hold.  If num_rendered > capacity nothing is
+ * written out of bounds, the outputs are unspecified, and the caller must call this
+ * function again with larger buffers (stage 1 need not be repeated).
+ * Outputs: out_color[3,H,W], out_others[8,H,W] (depth, alpha, normal xyz, median
+ * depth, distortion, median weight -- auxiliary.h:25-30). */
+int srf_forward_render(srf_stream_t stream, int P, int image_height, int image_width,
+                       size_t capacity, const void* geom_state, void* tile_state,
+                       void* entries, uint32_t* point_list, void* image_state,
+                       const float* background, float* out_color, float* out_others);
+
+/* ---- backward ------------------------------------------------------------------
+ * Replaces Rasterizer::backward (rasterizer_impl.cu:346-448): BACKWARD::render,
+ * computeAABB backward, BACKWARD::preprocess.  Consumes the state the forward left in
+ * geom/tile/image workspaces and point_list.  Output pointers may be NULL when that
+ * gradient is not wanted (dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations are
+ * required).  Every non-NULL output row is written (zeros for culled Gaussians), so
+ * the outputs need no initialisation -- unless accumulate != 0, in which case the
+ * kernel adds into them (used to sum several views before one all-reduce).
+ *   dL_dmeans2D[P,3] receives the reference's densification statistic
+ *   (backward.cu:645-648), dL_dcolors[P,3] the gradient wrt the (pre-clamp) RGB,
+ *   dL_dtransMat[P,9] the gradient wrt the homography (cov3D_precomp slot).          */
+int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int image_width,
+                 size_t capacity, const float* background,
+                 const float* means3D, const float* shs, int colors_were_precomputed,
+                 const float* scales, const float* rotations, int transmat_was_precomputed,
+                 const float* viewmatrix, const float* projmatrix, const float* campos,
+                 float tan_fovx, float tan_fovy, const int* radii,
+                 const void* geom_state, const void* tile_state, const uint32_t* point_list,
+                 const void* image_state,
+                 const float* dL_dout_color, const float* dL_dout_others,
+                 void* scratch, int accumulate,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat);
+
+/* ---- markVisible (DSR/rasterize_points.cu:242-261, rasterizer_impl.cu:141-153) ----
+ * present[i] = 1 iff the view-space z of means3D[i] is > 0.2 (one byte per Gaussian). */
+int srf_mark_visible(srf_stream_t stream, int P, const float* means3D,
+                     const float* viewmatrix, const float* projmatrix, uint8_t* present);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFEL_RASTERIZER_H_ */

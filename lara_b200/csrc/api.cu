@@ -1,0 +1,331 @@
+// api.cu -- the extern "C" boundary declared in include/surfel_rasterizer.h.
+// Plain pointers and sizes in, int status out; only enqueues work on the given stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/surfel_rasterizer.h"
+#include "surfel_common.cuh"
+#include "surfel_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+int cuda_fail(const char* what, cudaError_t e) {
+    return fail("%s: %s", what, cudaGetErrorString(e));
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GeomLayout { size_t rec, depths, rects, total; };
+struct TileLayout { size_t count, counters, ranges, cursor, big, total; int gx, gy, ntiles; };
+struct ImageLayout { size_t accum, ncontrib, total; };
+
+GeomLayout geom_layout(int P) {
+    GeomLayout l;
+    const size_t p = (size_t)(P > 0 ? P : 0);
+    size_t o = 0;
+    l.rec = o; o = align_up(o + p * SRF_REC_QUADS * sizeof(float4));
+    l.depths = o; o = align_up(o + p * sizeof(float));
+    l.rects = o; o = align_up(o + p * sizeof(uint2));
+    l.total = o + 256;
+    return l;
+}
+
+TileLayout tile_layout(int H, int W) {
+    TileLayout l;
+    l.gx = (W + SRF_TILE - 1) / SRF_TILE;
+    l.gy = (H + SRF_TILE - 1) / SRF_TILE;
+    l.ntiles = l.gx * l.gy;
+    const size_t n = (size_t)l.ntiles;
+    size_t o = 0;
+    l.count = o; o += n * sizeof(uint32_t);
+    o = (o + 15) / 16 * 16;
+    l.counters = o; o = align_up(o + 4 * sizeof(uint32_t));   // count+counters are zeroed by one memset
+    l.ranges = o; o = align_up(o + n * sizeof(uint2));
+    l.cursor = o; o = align_up(o + n * sizeof(uint32_t));
+    l.big = o; o = align_up(o + n * sizeof(uint32_t));
+    l.total = o + 256;
+    return l;
+}
+
+ImageLayout image_layout(int H, int W) {
+    ImageLayout l;
+    const size_t npix = (size_t)H * W;
+    size_t o = 0;
+    l.accum = o; o = align_up(o + 3 * npix * sizeof(float));
+    l.ncontrib = o; o = align_up(o + 2 * npix * sizeof(uint32_t));
+    l.total = o + 256;
+    return l;
+}
+
+template <typename T>
+T* at(const void* base, size_t off) {
+    return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(base) + off);
+}
+
+bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 255) != 0; }
+
+}  // namespace
+
+extern "C" {
+
+int srf_abi_version(void) { return SRF_ABI_VERSION; }
+const char* srf_last_error(void) { return g_err; }
+
+int srf_geom_state_bytes(int P, size_t* bytes) {
+    if (P < 0 || !bytes) return fail("srf_geom_state_bytes: bad arguments");
+    *bytes = geom_layout(P).total;
+    return 0;
+}
+
+int srf_tile_state_bytes(int H, int W, size_t* bytes) {
+    if (H <= 0 || W <= 0 || !bytes) return fail("srf_tile_state_bytes: bad arguments");
+    *bytes = tile_layout(H, W).total;
+    return 0;
+}
+
+int srf_image_state_bytes(int H, int W, size_t* bytes) {
+    if (H <= 0 || W <= 0 || !bytes) return fail("srf_image_state_bytes: bad arguments");
+    *bytes = image_layout(H, W).total;
+    return 0;
+}
+
+int srf_binning_bytes(size_t capacity, size_t* entries_bytes, size_t* point_list_bytes) {
+    if (!entries_bytes || !point_list_bytes) return fail("srf_binning_bytes: bad arguments");
+    *entries_bytes = align_up(capacity * sizeof(uint64_t)) + 256;
+    *point_list_bytes = align_up(capacity * sizeof(uint32_t)) + 256;
+    return 0;
+}
+
+int srf_backward_scratch_bytes(int P, size_t* bytes) {
+    if (P < 0 || !bytes) return fail("srf_backward_scratch_bytes: bad arguments");
+    *bytes = align_up((size_t)P * SRF_GRAD_FLOATS * sizeof(float)) + 256;
+    return 0;
+}
+
+int srf_state_layout(int P, int H, int W, size_t geom_off[3], size_t tile_off[5], size_t image_off[2]) {
+    if (P < 0 || H <= 0 || W <= 0) return fail("srf_state_layout: bad arguments");
+    const GeomLayout g = geom_layout(P);
+    const TileLayout t = tile_layout(H, W);
+    const ImageLayout i = image_layout(H, W);
+    if (geom_off) { geom_off[0] = g.rec; geom_off[1] = g.depths; geom_off[2] = g.rects; }
+    if (tile_off) { tile_off[0] = t.count; tile_off[1] = t.counters; tile_off[2] = t.ranges; tile_off[3] = t.cursor; tile_off[4] = t.big; }
+    if (image_off) { image_off[0] = i.accum; image_off[1] = i.ncontrib; }
+    return 0;
+}
+
+int srf_forward_preprocess(srf_stream_t stream_, int P, int D, int M,
+                           const float* means3D, const float* shs, const float* colors_precomp,
+                           const float* opacities, const float* scales, float scale_modifier,
+                           const float* rotations, const float* transMat_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* campos,
+                           float tan_fovx, float tan_fovy, int image_height, int image_width,
+                           int prefiltered, int* radii, void* geom_state, void* tile_state,
+                           uint32_t* num_rendered_host) {
+    (void)scale_modifier; (void)projmatrix;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_forward_preprocess: bad sizes");
+    if (image_height > 16 * 65535 || image_width > 16 * 65535) return fail("srf_forward_preprocess: image too large");
+    if (!tile_state || misaligned(tile_state)) return fail("srf_forward_preprocess: tile_state must be 256-byte aligned");
+    if (D < 0 || D > 3) return fail("srf_forward_preprocess: sh degree must be in [0,3]");
+    const TileLayout tl = tile_layout(image_height, image_width);
+    cudaError_t e = cudaMemsetAsync(at<char>(tile_state, tl.count), 0, tl.counters + 4 * sizeof(uint32_t) - tl.count, stream);
+    if (e != cudaSuccess) return cuda_fail("memset tile counters", e);
+
+    srf::BinArgs b;
+    memset(&b, 0, sizeof(b));
+    b.P = P; b.ntiles = tl.ntiles; b.gx = tl.gx;
+    b.tile_count = at<uint32_t>(tile_state, tl.count);
+    b.counters = at<uint32_t>(tile_state, tl.counters);
+    b.ranges = at<uint2>(tile_state, tl.ranges);
+    b.cursor = at<uint32_t>(tile_state, tl.cursor);
+    b.big_list = at<uint32_t>(tile_state, tl.big);
+
+    if (P > 0) {
+        if (!means3D || !opacities || !viewmatrix || !campos || !radii)
+            return fail("srf_forward_preprocess: null required pointer");
+        if ((shs == nullptr) == (colors_precomp == nullptr))
+            return fail("Please provide excatly one of either SHs or precomputed colors!");
+        if (((scales == nullptr || rotations == nullptr) && transMat_precomp == nullptr) ||
+            ((scales != nullptr || rotations != nullptr) && transMat_precomp != nullptr))
+            return fail("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        if (shs && M < (D + 1) * (D + 1)) return fail("srf_forward_preprocess: M=%d SH coefficients < (D+1)^2 for D=%d", M, D);
+        if (!geom_state || misaligned(geom_state)) return fail("srf_forward_preprocess: geom_state must be 256-byte aligned");
+        if ((reinterpret_cast<uintptr_t>(rotations) & 15) || (reinterpret_cast<uintptr_t>(scales) & 7))
+            return fail("srf_forward_preprocess: rotations must be 16-byte and scales 8-byte aligned");
+        const GeomLayout gl = geom_layout(P);
+        srf::PreprocessArgs a;
+        memset(&a, 0, sizeof(a));
+        a.P = P; a.D = D; a.M = shs ? M : 0;
+        a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities;
+        a.shs = shs; a.transMat_precomp = transMat_precomp; a.colors_precomp = colors_precomp;
+        a.viewmatrix = viewmatrix; a.campos = campos;
+        a.W = image_width; a.H = image_height;
+        a.focal_y = image_height / (2.0f * tan_fovy);   // rasterizer_impl.cu:223-224
+        a.focal_x = image_width / (2.0f * tan_fovx);
+        a.gx = tl.gx; a.gy = tl.gy;
+        a.prefiltered = prefiltered;
+        a.radii = radii;
+        a.rec = at<float4>(geom_state, gl.rec);
+        a.depths = at<float>(geom_state, gl.depths);
+        a.rects = at<uint2>(geom_state, gl.rects);
+        a.tile_count = b.tile_count;
+        e = srf::launch_preprocess_fwd(a, stream);
+        if (e != cudaSuccess) return cuda_fail("preprocess_fwd launch", e);
+    }
+    e = srf::launch_tile_scan(b, stream);
+    if (e != cudaSuccess) return cuda_fail("tile_scan launch", e);
+    if (num_rendered_host) {
+        e = cudaMemcpyAsync(num_rendered_host, b.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return cuda_fail("num_rendered copy", e);
+    }
+    return 0;
+}
+
+int srf_forward_render(srf_stream_t stream_, int P, int image_height, int image_width,
+                       size_t capacity, const void* geom_state, void* tile_state,
+                       void* entries, uint32_t* point_list, void* image_state,
+                       const float* background, float* out_color, float* out_others) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_forward_render: bad sizes");
+    if (!tile_state || !image_state || !background || !out_color || !out_others)
+        return fail("srf_forward_render: null required pointer");
+    if (capacity > 0xfffffff0ull) return fail("srf_forward_render: capacity exceeds 32-bit instance indices");
+    if (capacity > 0 && (!entries || !point_list)) return fail("srf_forward_render: null binning buffers");
+    const TileLayout tl = tile_layout(image_height, image_width);
+    const ImageLayout il = image_layout(image_height, image_width);
+    const GeomLayout gl = geom_layout(P);
+
+    srf::BinArgs b;
+    memset(&b, 0, sizeof(b));
+    b.P = P; b.ntiles = tl.ntiles; b.gx = tl.gx;
+    b.capacity = (uint32_t)capacity;
+    b.tile_count = at<uint32_t>(tile_state, tl.count);
+    b.counters = at<uint32_t>(tile_state, tl.counters);
+    b.ranges = at<uint2>(tile_state, tl.ranges);
+    b.cursor = at<uint32_t>(tile_state, tl.cursor);
+    b.big_list = at<uint32_t>(tile_state, tl.big);
+    b.entries = static_cast<uint64_t*>(entries);
+    b.point_list = point_list;
+    cudaError_t e;
+    if (P > 0) {
+        if (!geom_state) return fail("srf_forward_render: null geom_state");
+        // culled Gaussians carry an empty rect, so the radii array is not needed here
+        b.depths = at<float>(geom_state, gl.depths);
+        b.rects = at<uint2>(geom_state, gl.rects);
+        e = srf::launch_bin_and_sort(b, stream);
+        if (e != cudaSuccess) return cuda_fail("binning launch", e);
+    }
+    srf::RenderFwdArgs r;
+    memset(&r, 0, sizeof(r));
+    r.W = image_width; r.H = image_height; r.gx = tl.gx; r.gy = tl.gy;
+    r.capacity = (uint32_t)capacity;
+    r.ranges = b.ranges;
+    r.point_list = point_list;
+    r.rec = P > 0 ? at<float4>(geom_state, gl.rec) : nullptr;
+    r.bg = background;
+    r.out_color = out_color; r.out_others = out_others;
+    r.accum = at<float>(image_state, il.accum);
+    r.n_contrib = at<uint32_t>(image_state, il.ncontrib);
+    e = srf::launch_render_fwd(r, stream);
+    if (e != cudaSuccess) return cuda_fail("render_fwd launch", e);
+    return 0;
+}
+
+int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, int image_width,
+                 size_t capacity, const float* background,
+                 const float* means3D, const float* shs, int colors_were_precomputed,
+                 const float* scales, const float* rotations, int transmat_was_precomputed,
+                 const float* viewmatrix, const float* projmatrix, const float* campos,
+                 float tan_fovx, float tan_fovy, const int* radii,
+                 const void* geom_state, const void* tile_state, const uint32_t* point_list,
+                 const void* image_state,
+                 const float* dL_dout_color, const float* dL_dout_others,
+                 void* scratch, int accumulate,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat) {
+    (void)projmatrix;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_backward: bad sizes");
+    if (P == 0) return 0;
+    if (!geom_state || !tile_state || !image_state || !scratch || !radii || !background)
+        return fail("srf_backward: null state pointer");
+    if (!dL_dout_color || !dL_dout_others) return fail("srf_backward: null upstream gradient");
+    if (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations)
+        return fail("srf_backward: null required output gradient");
+    if (!means3D || !viewmatrix || !campos) return fail("srf_backward: null input pointer");
+    if (!transmat_was_precomputed && (!scales || !rotations)) return fail("srf_backward: scales/rotations required");
+    if (misaligned(scratch)) return fail("srf_backward: scratch must be 256-byte aligned");
+    const TileLayout tl = tile_layout(image_height, image_width);
+    const ImageLayout il = image_layout(image_height, image_width);
+    const GeomLayout gl = geom_layout(P);
+
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)P * SRF_GRAD_FLOATS * sizeof(float), stream);
+    if (e != cudaSuccess) return cuda_fail("memset gradient records", e);
+
+    srf::RenderBwdArgs r;
+    memset(&r, 0, sizeof(r));
+    r.W = image_width; r.H = image_height; r.gx = tl.gx; r.gy = tl.gy;
+    r.capacity = (uint32_t)capacity;
+    r.ranges = at<uint2>(tile_state, tl.ranges);
+    r.point_list = point_list;
+    r.rec = at<float4>(geom_state, gl.rec);
+    r.bg = background;
+    r.accum = at<float>(image_state, il.accum);
+    r.n_contrib = at<uint32_t>(image_state, il.ncontrib);
+    r.dL_dpix = dL_dout_color;
+    r.dL_dothers = dL_dout_others;
+    r.ggrad = static_cast<float*>(scratch);
+    e = srf::launch_render_bwd(r, stream);
+    if (e != cudaSuccess) return cuda_fail("render_bwd launch", e);
+
+    srf::PreprocessBwdArgs p;
+    memset(&p, 0, sizeof(p));
+    p.P = P; p.D = D; p.M = (shs && !colors_were_precomputed) ? M : 0;
+    p.means3D = means3D; p.scales = scales; p.rotations = rotations;
+    p.shs = colors_were_precomputed ? nullptr : shs;
+    p.viewmatrix = viewmatrix; p.campos = campos;
+    p.W = image_width; p.H = image_height;
+    p.focal_y = image_height / (2.0f * tan_fovy);
+    p.focal_x = image_width / (2.0f * tan_fovx);
+    p.tan_fovx = tan_fovx; p.tan_fovy = tan_fovy;
+    p.has_precomp_T = transmat_was_precomputed ? 1 : 0;
+    p.has_precomp_color = colors_were_precomputed ? 1 : 0;
+    p.radii = radii;
+    p.rec = r.rec;
+    p.ggrad = r.ggrad;
+    p.accumulate = accumulate ? 1 : 0;
+    p.dL_dmeans3D = dL_dmeans3D; p.dL_dmeans2D = dL_dmeans2D;
+    p.dL_dsh = p.M > 0 ? dL_dsh : nullptr;
+    p.dL_dcolors = dL_dcolors; p.dL_dopacity = dL_dopacity;
+    p.dL_dscales = dL_dscales; p.dL_drotations = dL_drotations; p.dL_dtransMat = dL_dtransMat;
+    e = srf::launch_preprocess_bwd(p, stream);
+    if (e != cudaSuccess) return cuda_fail("preprocess_bwd launch", e);
+    return 0;
+}
+
+int srf_mark_visible(srf_stream_t stream_, int P, const float* means3D,
+                     const float* viewmatrix, const float* projmatrix, uint8_t* present) {
+    (void)projmatrix;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0) return fail("srf_mark_visible: bad P");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !present) return fail("srf_mark_visible: null pointer");
+    cudaError_t e = srf::launch_mark_visible(P, means3D, viewmatrix, present, stream);
+    if (e != cudaSuccess) return cuda_fail("mark_visible launch", e);
+    return 0;
+}
+
+}  // extern "C"

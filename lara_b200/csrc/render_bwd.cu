@@ -1,0 +1,300 @@
+// render_bwd.cu -- reverse-order per-pixel backward of the blend (K7).
+// Replaces reference backward.cu:143-449 (renderCUDA backward).
+//
+// Same tiling as the forward: one CTA per 16x16 tile, one thread per pixel, the tile's
+// list walked back-to-front in shared-memory batches of 256 splats.  The reference emits
+// 10-16 global float atomics per (pixel, splat) pair, 256 threads hammering the same
+// <=18 addresses.  Here each warp first transposes-and-reduces the 18 partial
+// derivatives of a splat across its 32 lanes with a 20-shuffle reduce-scatter
+// (9+5+3+2+1), adds the warp totals into a per-batch shared-memory accumulator
+// (bank-conflict-free, 18 consecutive words per splat) and the CTA finally issues at
+// most five 128-bit vector reductions (red.global.add.v4.f32) per splat per tile.
+// Further savings the reference does not have:
+//   * the walk starts at the tile's last *used* list entry (max n_contrib over the
+//     tile) instead of the end of the list,
+//   * warp-uniform skips: entries beyond the warp's deepest contributor, and splats
+//     that no lane of the warp touches, cost no reduction traffic at all.
+#include "surfel_common.cuh"
+#include "surfel_kernels.h"
+
+namespace srf {
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// Reduce-scatter of 18 per-lane values over the warp.  Returns in `out` the warp total of
+// value `index` (index in [0,18)) or index = -1 on lanes that end up holding padding.
+__device__ __forceinline__ void warp_reduce_scatter18(const float (&v)[18], int lane, float& out, int& index) {
+    const unsigned full = 0xffffffffu;
+    const bool u4 = (lane & 16) != 0;
+    float a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const float keep = u4 ? v[9 + i] : v[i];
+        const float send = u4 ? v[i] : v[9 + i];
+        a[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+    int base = u4 ? 9 : 0;
+    int size = 9;
+    const bool u3 = (lane & 8) != 0;
+    float b[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float hi = (5 + i < 9) ? a[5 + i] : 0.0f;
+        const float keep = u3 ? hi : a[i];
+        const float send = u3 ? a[i] : hi;
+        b[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    base += u3 ? 5 : 0;
+    size = u3 ? max(size - 5, 0) : min(size, 5);
+    const bool u2 = (lane & 4) != 0;
+    float c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float hi = (3 + i < 5) ? b[3 + i] : 0.0f;
+        const float keep = u2 ? hi : b[i];
+        const float send = u2 ? b[i] : hi;
+        c[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    base += u2 ? 3 : 0;
+    size = u2 ? max(size - 3, 0) : min(size, 3);
+    const bool u1 = (lane & 2) != 0;
+    float d[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float hi = (2 + i < 3) ? c[2 + i] : 0.0f;
+        const float keep = u1 ? hi : c[i];
+        const float send = u1 ? c[i] : hi;
+        d[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    base += u1 ? 2 : 0;
+    size = u1 ? max(size - 2, 0) : min(size, 2);
+    const bool u0 = (lane & 1) != 0;
+    {
+        const float keep = u0 ? d[1] : d[0];
+        const float send = u0 ? d[0] : d[1];
+        out = keep + __shfl_xor_sync(full, send, 1);
+    }
+    base += u0 ? 1 : 0;
+    size = u0 ? max(size - 1, 0) : min(size, 1);
+    index = size > 0 ? base : -1;
+}
+
+__global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
+    __shared__ float4 s_rec[SRF_REC_QUADS - 1][256];
+    __shared__ __align__(16) float s_grad[256 * SRF_GRAD_FLOATS];
+    __shared__ uint32_t s_id[256];
+    __shared__ int s_touched[256];
+    __shared__ int s_wmax[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
+    const bool inside = pxi < a.W && pyi < a.H;
+    const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
+    const size_t npix = (size_t)a.W * a.H;
+    const size_t pix = (size_t)pyi * a.W + pxi;
+
+    uint2 range = a.ranges[tile];
+    if (range.y > a.capacity) range.y = range.x;
+
+    const float T_final = inside ? a.accum[pix] : 0.0f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)a.n_contrib[pix] : 0;
+    const int median_contributor = inside ? (int)a.n_contrib[pix + npix] : 0;
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f;
+    float dL_ddepth = 0.f, dL_daccum = 0.f, dL_dreg = 0.f, dn0 = 0.f, dn1 = 0.f, dn2 = 0.f;
+    float dL_dmedian_depth = 0.f, dL_dmax_dweight = 0.f;
+    float final_D = 0.f, final_D2 = 0.f;
+    if (inside) {
+        dpix0 = a.dL_dpix[pix]; dpix1 = a.dL_dpix[pix + npix]; dpix2 = a.dL_dpix[pix + 2 * npix];
+        dL_ddepth = a.dL_dothers[pix];
+        dL_daccum = a.dL_dothers[pix + npix];
+        dn0 = a.dL_dothers[pix + 2 * npix];
+        dn1 = a.dL_dothers[pix + 3 * npix];
+        dn2 = a.dL_dothers[pix + 4 * npix];
+        dL_dmedian_depth = a.dL_dothers[pix + 5 * npix];
+        dL_dreg = a.dL_dothers[pix + 6 * npix];
+        dL_dmax_dweight = a.dL_dothers[pix + 7 * npix];
+        final_D = a.accum[pix + npix];
+        final_D2 = a.accum[pix + 2 * npix];
+    }
+    const float final_A = 1.0f - T_final;
+    const float bg_dot_dpixel = __ldg(a.bg + 0) * dpix0 + __ldg(a.bg + 1) * dpix1 + __ldg(a.bg + 2) * dpix2;
+
+    // deepest list entry any pixel of the warp / of the tile blended
+    int wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_wmax[wid] = wmax;
+    __syncthreads();
+    int n_eff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n_eff = max(n_eff, s_wmax[w]);
+    const int rounds = (n_eff + 255) >> 8;
+
+    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;        // accum_rec
+    float last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;     // last_color
+    float last_alpha = 0.f, last_depth = 0.f;
+    float last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f;
+    float acc_depth = 0.f, acc_alpha = 0.f, acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
+    float last_dL_dT = 0.f;
+
+    for (int b = 0; b < rounds; ++b) {
+        // stage batch b (back to front) and clear the accumulator rows this thread owns
+        const int pos_mine = n_eff - 1 - (b * 256 + tid);
+        if (pos_mine >= 0) {
+            const uint32_t id = __ldg(a.point_list + range.x + pos_mine);
+            s_id[tid] = id;
+            const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
+#pragma unroll
+            for (int k = 0; k < SRF_REC_QUADS - 1; ++k) s_rec[k][tid] = ldg4(r + k);
+        }
+        {
+            float4* g4 = reinterpret_cast<float4*>(s_grad + tid * SRF_GRAD_FLOATS);
+#pragma unroll
+            for (int k = 0; k < SRF_GRAD_FLOATS / 4; ++k) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_touched[tid] = 0;
+        }
+        __syncthreads();
+
+        const int cnt = min(256, n_eff - b * 256);
+        for (int j = 0; j < cnt; ++j) {
+            const int pos = n_eff - 1 - (b * 256 + j);   // 0-based position in the tile list
+            if (pos >= wmax) continue;                    // warp-uniform
+            bool contrib = inside && pos < last_contributor;
+            PairEval e;
+            const float4 q0 = s_rec[0][j], q1 = s_rec[1][j], q2 = s_rec[2][j];
+            if (contrib) {
+                eval_pair(q0, q1, q2, pixx, pixy, e);
+                contrib = e.valid;
+            }
+            if (!__any_sync(0xffffffffu, contrib)) continue;
+
+            float g[18];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) g[i] = 0.0f;
+
+            if (contrib) {
+                const float4 q3 = s_rec[3][j];
+                const float4 q4 = s_rec[4][j];
+                const float alpha = e.alpha, G = e.G, c_d = e.depth;
+                const float Twx = q1.z, Twy = q1.w;
+                const float opac = q2.w;
+
+                T = T / (1.0f - alpha);
+                const float w = alpha * T;  // dchannel_dcolor
+                float dL_dalpha = 0.0f;
+                // colour (backward.cu:331-346)
+                acc_c0 = last_alpha * last_c0 + (1.f - last_alpha) * acc_c0; last_c0 = q4.x;
+                acc_c1 = last_alpha * last_c1 + (1.f - last_alpha) * acc_c1; last_c1 = q4.y;
+                acc_c2 = last_alpha * last_c2 + (1.f - last_alpha) * acc_c2; last_c2 = q4.z;
+                dL_dalpha += (q4.x - acc_c0) * dpix0;
+                dL_dalpha += (q4.y - acc_c1) * dpix1;
+                dL_dalpha += (q4.z - acc_c2) * dpix2;
+                g[SRF_G_DCOLOR + 0] = w * dpix0;
+                g[SRF_G_DCOLOR + 1] = w * dpix1;
+                g[SRF_G_DCOLOR + 2] = w * dpix2;
+
+                float dL_dz = 0.0f, dL_dweight = 0.0f;
+                // distortion / median terms (backward.cu:350-368); double constants as the reference
+                const double cd = (double)c_d;
+                const float m_d = (float)((100.0 * cd - 100.0 * 0.2) / ((100.0 - 0.2) * cd));
+                const float dmd_dd = (float)((100.0 * 0.2) / ((100.0 - 0.2) * cd * cd));
+                if (pos == median_contributor - 1) {
+                    dL_dz += dL_dmedian_depth;
+                    dL_dweight += dL_dmax_dweight;
+                }
+                dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
+                dL_dalpha += dL_dweight - last_dL_dT;
+                last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
+                const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                dL_dz += dL_dmd * dmd_dd;
+                // depth / alpha / normal maps (backward.cu:370-385)
+                acc_depth = last_alpha * last_depth + (1.f - last_alpha) * acc_depth;
+                last_depth = c_d;
+                dL_dalpha += (c_d - acc_depth) * dL_ddepth;
+                acc_alpha = last_alpha * 1.0f + (1.f - last_alpha) * acc_alpha;
+                dL_dalpha += (1.0f - acc_alpha) * dL_daccum;
+                acc_n0 = last_alpha * last_n0 + (1.f - last_alpha) * acc_n0; last_n0 = q3.x;
+                acc_n1 = last_alpha * last_n1 + (1.f - last_alpha) * acc_n1; last_n1 = q3.y;
+                acc_n2 = last_alpha * last_n2 + (1.f - last_alpha) * acc_n2; last_n2 = q3.z;
+                dL_dalpha += (q3.x - acc_n0) * dn0;
+                dL_dalpha += (q3.y - acc_n1) * dn1;
+                dL_dalpha += (q3.z - acc_n2) * dn2;
+                g[SRF_G_DNORMAL + 0] = w * dn0;
+                g[SRF_G_DNORMAL + 1] = w * dn1;
+                g[SRF_G_DNORMAL + 2] = w * dn2;
+
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                // background term (backward.cu:391-396)
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                const float dL_dG = opac * dL_dalpha;
+                dL_dz += w * dL_ddepth;
+
+                if (e.rho3d <= e.rho2d) {
+                    // ray-splat branch: vjp through s = p.xy / p.z, p = k x l (backward.cu:405-435)
+                    const float dL_dsx = dL_dG * -G * e.sx + dL_dz * Twx;
+                    const float dL_dsy = dL_dG * -G * e.sy + dL_dz * Twy;
+                    const float dsx_pz = dL_dsx / e.pz;
+                    const float dsy_pz = dL_dsy / e.pz;
+                    const float dpx = dsx_pz, dpy = dsy_pz, dpz = -(dsx_pz * e.sx + dsy_pz * e.sy);
+                    // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
+                    const float dkx = e.ly * dpz - e.lz * dpy;
+                    const float dky = e.lz * dpx - e.lx * dpz;
+                    const float dkz = e.lx * dpy - e.ly * dpx;
+                    const float dlx = dpy * e.kz - dpz * e.ky;
+                    const float dly = dpz * e.kx - dpx * e.kz;
+                    const float dlz = dpx * e.ky - dpy * e.kx;
+                    g[SRF_G_DT + 0] = -dkx; g[SRF_G_DT + 1] = -dky; g[SRF_G_DT + 2] = -dkz;
+                    g[SRF_G_DT + 3] = -dlx; g[SRF_G_DT + 4] = -dly; g[SRF_G_DT + 5] = -dlz;
+                    g[SRF_G_DT + 6] = pixx * dkx + pixy * dlx + dL_dz * e.sx;
+                    g[SRF_G_DT + 7] = pixx * dky + pixy * dly + dL_dz * e.sy;
+                    g[SRF_G_DT + 8] = pixx * dkz + pixy * dlz + dL_dz;
+                } else {
+                    // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
+                    const float dG_ddelx = -G * 2.0f * e.dx;
+                    const float dG_ddely = -G * 2.0f * e.dy;
+                    g[SRF_G_DMEAN2D + 0] = dL_dG * dG_ddelx;
+                    g[SRF_G_DMEAN2D + 1] = dL_dG * dG_ddely;
+                    g[SRF_G_DT + 8] = dL_dz;
+                }
+                g[SRF_G_DOPAC] = G * dL_dalpha;
+            }
+
+            float total;
+            int index;
+            warp_reduce_scatter18(g, lane, total, index);
+            if (index >= 0) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + index], total);
+            if (lane == 0) s_touched[j] = 1;
+        }
+        __syncthreads();
+
+        // flush: one thread per staged splat, five 128-bit vector reductions
+        if (pos_mine >= 0 && s_touched[tid]) {
+            const float4* g4 = reinterpret_cast<const float4*>(s_grad + tid * SRF_GRAD_FLOATS);
+            float* dst = a.ggrad + (size_t)s_id[tid] * SRF_GRAD_FLOATS;
+#pragma unroll
+            for (int k = 0; k < SRF_GRAD_FLOATS / 4; ++k) red_add_v4(dst + 4 * k, g4[k]);
+        }
+        // (the same thread re-zeroes its row and restages its slot at the top of the loop;
+        //  s_rec rows are protected by the barrier above)
+    }
+}
+
+cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
+    const int ntiles = a.gx * a.gy;
+    if (ntiles <= 0) return cudaSuccess;
+    render_bwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace srf

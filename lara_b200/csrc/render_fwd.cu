@@ -1,0 +1,124 @@
+// render_fwd.cu -- per-tile front-to-back alpha compositing (K6).
+// Replaces reference forward.cu:265-463 (renderCUDA forward).
+//
+// One 256-thread CTA per 16x16 tile, one thread per pixel (each warp owns an 8x4 pixel
+// block).  The tile's depth-sorted Gaussian list is consumed in batches of 256: every
+// thread gathers one 96 B GeomRecord with six 128-bit loads and stages it in shared
+// memory as six float4 planes, so the inner loop reads each splat with broadcast
+// LDS.128 (no bank conflicts) and never touches global memory -- including the colour,
+// which the reference fetches from global memory per contributing pixel.
+// Arithmetic and predicates follow the reference exactly (see eval_pair()).
+#include "surfel_common.cuh"
+#include "surfel_kernels.h"
+
+namespace srf {
+
+__global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
+    __shared__ float4 s_rec[SRF_REC_QUADS - 1][256];  // q0..q4 (q5 is not needed by the blend)
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
+    const bool inside = pxi < a.W && pyi < a.H;
+    const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
+
+    uint2 range = a.ranges[tile];
+    if (range.y > a.capacity) range.y = range.x;  // overflowed optimistic capacity: host re-runs
+    const int n = (int)(range.y - range.x);
+    const int rounds = (n + 255) >> 8;
+
+    bool done = !inside;
+    float T = 1.0f;
+    uint32_t contributor = 0, last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float D = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
+    float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
+    float median_depth = 0.f, median_weight = 0.f, median_contributor = -1.0f;
+
+    int todo = n;
+    for (int b = 0; b < rounds; ++b, todo -= 256) {
+        // whole tile saturated -> stop (reference forward.cu:334-336)
+        if (__syncthreads_count(done) == 256) break;
+        const int progress = b * 256 + tid;
+        if (progress < n) {
+            const uint32_t id = __ldg(a.point_list + range.x + progress);
+            const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
+#pragma unroll
+            for (int k = 0; k < SRF_REC_QUADS - 1; ++k) s_rec[k][tid] = ldg4(r + k);
+        }
+        __syncthreads();
+        const int cnt = min(256, todo);
+        // warp-uniform skip: a fully saturated warp only helps with staging
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int j = 0; !done && j < cnt; ++j) {
+            contributor++;
+            PairEval e;
+            eval_pair(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
+            if (!e.valid) continue;
+            const float alpha = e.alpha;
+            const float test_T = fmul_(T, fadd_(1.0f, -alpha));
+            if (!(test_T >= 0.0001f)) {
+                done = true;
+                continue;
+            }
+            const float4 q3 = s_rec[3][j];
+            const float4 q4 = s_rec[4][j];
+            const float depth = e.depth;
+            const float A = fadd_(1.0f, -T);
+            const float m = mapped_depth(depth);
+            const float mm = fmul_(m, m);
+            const float err = fma_(-dist1, fadd_(m, m), fma_(A, mm, dist2));
+            distortion = fma_(T, fmul_(alpha, err), distortion);
+            if (T > 0.5f) {
+                median_depth = depth;
+                median_weight = fmul_(T, alpha);
+                median_contributor = (float)contributor;
+            }
+            N0 = fma_(T, fmul_(q3.x, alpha), N0);
+            N1 = fma_(T, fmul_(q3.y, alpha), N1);
+            N2 = fma_(T, fmul_(q3.z, alpha), N2);
+            D = fma_(T, fmul_(depth, alpha), D);
+            dist1 = fma_(T, fmul_(alpha, m), dist1);
+            dist2 = fma_(T, fmul_(alpha, mm), dist2);
+            C0 = fma_(T, fmul_(alpha, q4.x), C0);
+            C1 = fma_(T, fmul_(alpha, q4.y), C1);
+            C2 = fma_(T, fmul_(alpha, q4.z), C2);
+            T = test_T;
+            last_contributor = contributor;
+        }
+    }
+
+    if (inside) {
+        const size_t npix = (size_t)a.W * a.H;
+        const size_t pix = (size_t)pyi * a.W + pxi;
+        a.accum[pix] = T;
+        a.accum[pix + npix] = dist1;
+        a.accum[pix + 2 * npix] = dist2;
+        a.n_contrib[pix] = last_contributor;
+        // float -> u32 conversion saturates -1 to 0, as the reference's implicit cast does
+        a.n_contrib[pix + npix] = (uint32_t)__float2uint_rz(median_contributor);
+        a.out_color[pix] = fma_(__ldg(a.bg + 0), T, C0);
+        a.out_color[pix + npix] = fma_(__ldg(a.bg + 1), T, C1);
+        a.out_color[pix + 2 * npix] = fma_(__ldg(a.bg + 2), T, C2);
+        a.out_others[pix] = D;
+        a.out_others[pix + npix] = fadd_(1.0f, -T);
+        a.out_others[pix + 2 * npix] = N0;
+        a.out_others[pix + 3 * npix] = N1;
+        a.out_others[pix + 4 * npix] = N2;
+        a.out_others[pix + 5 * npix] = median_depth;
+        a.out_others[pix + 6 * npix] = distortion;
+        a.out_others[pix + 7 * npix] = median_weight;
+    }
+}
+
+cudaError_t launch_render_fwd(const RenderFwdArgs& a, cudaStream_t stream) {
+    const int ntiles = a.gx * a.gy;
+    if (ntiles <= 0) return cudaSuccess;
+    render_fwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace srf

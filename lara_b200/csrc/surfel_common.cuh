@@ -1,0 +1,116 @@
+// surfel_common.cuh -- shared device definitions of the B200 surfel rasterizer.
+//
+// Data layout in HBM (all produced by the forward, consumed by render fwd/bwd and the
+// backward preprocess; see DESIGN.md "Data layout"):
+//
+//   GeomRecord  : 6 x float4 = 96 B per Gaussian, record-major, 32 B aligned so one
+//                 gather touches exactly three DRAM sectors.
+//       q0 = Tu.x Tu.y Tu.z Tv.x          (rows of the splat->screen homography T,
+//       q1 = Tv.y Tv.z Tw.x Tw.y           reference forward.cu:75-128)
+//       q2 = Tw.z cx   cy   opacity       (cx,cy = screen-space AABB centre)
+//       q3 = n.x  n.y  n.z  depth         (view-space normal, view-space z)
+//       q4 = r    g    b    clamp-bits    (SH->RGB colour, 3 clamp flags as int bits)
+//       q5 = reserved (warp-level cull data)
+//
+// Every float op on the integer-critical chain (depth bits -> sort key, T -> AABB ->
+// radius -> tile rect, and the per-pixel alpha/transmittance chain that decides
+// n_contrib) is written with explicit round-to-nearest intrinsics in exactly the
+// order nvcc 12.9 emitted for the reference (sm_100 SASS of forward.cu), so that
+// fused-multiply-add contraction cannot differ between the two builds.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SRF_TILE 16
+#define SRF_TILE_PIX 256
+#define SRF_REC_QUADS 6
+#define SRF_GRAD_FLOATS 20  // per-Gaussian gradient accumulation record (5 x float4)
+
+// gradient accumulation record layout (floats)
+#define SRF_G_DT 0        // 9: dL/dT
+#define SRF_G_DMEAN2D 9   // 2: dL/dmean2D (low-pass branch)
+#define SRF_G_DOPAC 11    // 1
+#define SRF_G_DNORMAL 12  // 3
+#define SRF_G_DCOLOR 15   // 3
+// 18,19: padding
+
+#define SRF_NEAR_F 0.2f
+
+__device__ __forceinline__ float fmul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// Result of intersecting one pixel ray with one splat (reference forward.cu:353-398,
+// backward.cu:258-318).  `valid` is false when the reference would `continue`.
+struct PairEval {
+    float kx, ky, kz, lx, ly, lz;  // the two homogeneous planes
+    float px, py, pz;              // their cross product (homogeneous splat point)
+    float sx, sy;                  // splat-space uv
+    float dx, dy;                  // centre - pixel
+    float rho3d, rho2d;
+    float depth;
+    float G;      // exp(-rho/2)
+    float alpha;  // min(0.99, opacity*G)
+    bool valid;
+};
+
+// The exact instruction sequence of the reference's per-(pixel,splat) evaluation.
+//   q0,q1,q2 : first three quads of the GeomRecord.
+__device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, const float4 q2,
+                                          const float pixx, const float pixy, PairEval& e) {
+    const float Tux = q0.x, Tuy = q0.y, Tuz = q0.z;
+    const float Tvx = q0.w, Tvy = q1.x, Tvz = q1.y;
+    const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
+    const float cx = q2.y, cy = q2.z, opac = q2.w;
+    e.valid = false;
+    // k = pix.x * Tw - Tu ; l = pix.y * Tw - Tv
+    e.kx = fma_(pixx, Twx, -Tux);
+    e.ky = fma_(pixx, Twy, -Tuy);
+    e.kz = fma_(pixx, Twz, -Tuz);
+    e.lx = fma_(pixy, Twx, -Tvx);
+    e.ly = fma_(pixy, Twy, -Tvy);
+    e.lz = fma_(pixy, Twz, -Tvz);
+    // p = k x l, each component fma(a,b,-(c*d))
+    e.pz = fma_(e.kx, e.ly, -fmul_(e.ky, e.lx));
+    e.px = fma_(e.ky, e.lz, -fmul_(e.kz, e.ly));
+    e.py = fma_(e.kz, e.lx, -fmul_(e.kx, e.lz));
+    if (e.pz == 0.0f) return;
+    e.sx = __fdiv_rn(e.px, e.pz);
+    e.sy = __fdiv_rn(e.py, e.pz);
+    e.rho3d = fma_(e.sx, e.sx, fmul_(e.sy, e.sy));
+    e.dx = fadd_(cx, -pixx);
+    e.dy = fadd_(cy, -pixy);
+    // FilterInvSquare * |d|^2 is evaluated in double by the reference; the double
+    // constant 1/(0.70710678118654762)^2 rounds the product to exactly 2*|d|^2 in fp32.
+    e.rho2d = fmul_(2.0f, fma_(e.dx, e.dx, fmul_(e.dy, e.dy)));
+    const float rho = fminf(e.rho3d, e.rho2d);
+    float depth = Twz;
+    if (e.rho3d <= e.rho2d) depth = fadd_(Twz, fma_(Twx, e.sx, fmul_(Twy, e.sy)));
+    e.depth = depth;
+    // reference compares (double)depth < 0.2 (double); identical to depth < 0.2f
+    if (!(depth >= SRF_NEAR_F)) return;
+    const float power = fmul_(rho, -0.5f);
+    if (power > 0.0f) return;
+    e.G = expf(power);
+    e.alpha = fminf(0.99f, fmul_(opac, e.G));
+    if (!(e.alpha >= 0.00392156862745098f)) return;  // alpha < 1/255
+    e.valid = true;
+}
+
+// mapped depth for the distortion loss, evaluated in double exactly as the reference
+// (forward.cu:412: (FAR*d - FAR*NEAR) / ((FAR-NEAR)*d), FAR=100.0, NEAR=0.2).
+__device__ __forceinline__ float mapped_depth(float depth) {
+    const double d = (double)depth;
+    const double num = __fma_rn(d, 100.0, -(100.0 * 0.2));   // DFMA in the reference SASS
+    const double den = __dmul_rn(100.0 - 0.2, d);
+    return (float)__ddiv_rn(num, den);
+}
+
+// pixel owned by thread `tid` of a 256-thread tile CTA: each warp covers an 8x4 block.
+__device__ __forceinline__ void tile_pixel(int tid, int& lx, int& ly) {
+    const int w = tid >> 5, l = tid & 31;
+    lx = ((w & 1) << 3) + (l & 7);
+    ly = ((w >> 1) << 2) + (l >> 3);
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }

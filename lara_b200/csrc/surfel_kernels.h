@@ -1,0 +1,111 @@
+// surfel_kernels.h -- internal (non-ABI) interface between the C-ABI layer (api.cu)
+// and the kernel translation units.  The public boundary is include/surfel_rasterizer.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace srf {
+
+struct PreprocessArgs {
+    int P, D, M;
+    const float* means3D;        // [P,3]
+    const float* scales;         // [P,2]
+    const float* rotations;      // [P,4] (w,x,y,z)
+    const float* opacities;      // [P]
+    const float* shs;            // [P,M,3] or null
+    const float* transMat_precomp;  // [P,9] or null
+    const float* colors_precomp;    // [P,3] or null
+    const float* viewmatrix;     // [16] column-major world->view
+    const float* campos;         // [3]
+    int W, H;
+    float focal_x, focal_y;
+    int gx, gy;                  // tile grid
+    int prefiltered;
+    int stage_sh;                // set by the launcher
+    int* radii;                  // [P] out
+    float4* rec;                 // [P*6] out
+    float* depths;               // [P] out
+    uint2* rects;                // [P] out: (x0 | y0<<16, x1 | y1<<16)
+    uint32_t* tile_count;        // [ntiles] in/out (zeroed by the caller)
+};
+
+struct BinArgs {
+    int P;
+    int ntiles;
+    int gx;
+    uint32_t capacity;           // number of instance slots in entries / point_list
+    const float* depths;
+    const uint2* rects;          // empty rect = culled
+    uint32_t* tile_count;        // [ntiles]
+    uint2* ranges;               // [ntiles] out
+    uint32_t* cursor;            // [ntiles] scratch
+    uint32_t* counters;          // [4]: num_rendered, big_count, overflow, spare
+    uint32_t* big_list;          // [ntiles] scratch
+    uint64_t* entries;           // [capacity] scratch: depth_bits<<32 | gaussian idx, bucketed by tile
+    uint32_t* point_list;        // [capacity] out: per-tile depth-sorted gaussian indices
+};
+
+struct RenderFwdArgs {
+    int W, H, gx, gy;
+    uint32_t capacity;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* rec;
+    const float* bg;             // [3] device
+    float* out_color;            // [3,H,W]
+    float* out_others;           // [8,H,W]
+    float* accum;                // [3,H,W]: final_T, dist1, dist2
+    uint32_t* n_contrib;         // [2,H,W]: last contributor, median contributor
+};
+
+struct RenderBwdArgs {
+    int W, H, gx, gy;
+    uint32_t capacity;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* rec;
+    const float* bg;
+    const float* accum;
+    const uint32_t* n_contrib;
+    const float* dL_dpix;        // [3,H,W]
+    const float* dL_dothers;     // [8,H,W]
+    float* ggrad;                // [P,20] zero-initialised accumulation records
+};
+
+struct PreprocessBwdArgs {
+    int P, D, M;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* shs;
+    const float* viewmatrix;
+    const float* campos;
+    int W, H;
+    float focal_x, focal_y, tan_fovx, tan_fovy;
+    int has_precomp_T;           // transMat_precomp was given: only dL_dtransMat is produced
+    int has_precomp_color;
+    const int* radii;
+    const float4* rec;
+    const float* ggrad;          // [P,20]
+    int accumulate;              // += into the outputs instead of overwriting (view-sharded accumulation)
+    float* dL_dmeans3D;          // [P,3]
+    float* dL_dmeans2D;          // [P,3] or null
+    float* dL_dsh;               // [P,M,3] or null
+    float* dL_dcolors;           // [P,3] or null
+    float* dL_dopacity;          // [P]
+    float* dL_dscales;           // [P,2]
+    float* dL_drotations;        // [P,4]
+    float* dL_dtransMat;         // [P,9] or null
+};
+
+cudaError_t launch_preprocess_fwd(const PreprocessArgs& a, cudaStream_t stream);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                                cudaStream_t stream);
+cudaError_t launch_tile_scan(const BinArgs& a, cudaStream_t stream);
+cudaError_t launch_bin_and_sort(const BinArgs& a, cudaStream_t stream);
+cudaError_t launch_render_fwd(const RenderFwdArgs& a, cudaStream_t stream);
+cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream);
+cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t stream);
+
+}  // namespace srf
