@@ -61,7 +61,8 @@ int srf_backward_scratch_bytes(int P, size_t* bytes);
 /* Byte offsets of the sub-arrays inside the workspaces (for tests / tooling that
  * inspect state the way the reference's blobs can be parsed).
  *   geom_off[3]  : rec, depths, rects
- *   tile_off[5]  : tile_count, counters(4 x u32: num_rendered, n_big, -, -), ranges(uint2), cursor, big_list
+ *   tile_off[5]  : tile blocks (one 256 B block per tile: u32 count, u32 cursor, padding),
+ *                  counters(4 x u32: num_rendered, n_big, -, -), ranges(uint2), first cursor, big_list
  *   image_off[2] : accum(3 float planes), n_contrib(2 u32 planes)                    */
 int srf_state_layout(int P, int H, int W, size_t geom_off[3], size_t tile_off[5], size_t image_off[2]);
 

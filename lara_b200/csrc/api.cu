@@ -29,7 +29,7 @@ int cuda_fail(const char* what, cudaError_t e) {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct GeomLayout { size_t rec, depths, rects, total; };
-struct TileLayout { size_t count, counters, ranges, cursor, big, total; int gx, gy, ntiles; };
+struct TileLayout { size_t count, counters, ranges, big, total; int gx, gy, ntiles; };
 struct ImageLayout { size_t accum, ncontrib, total; };
 
 GeomLayout geom_layout(int P) {
@@ -50,11 +50,9 @@ TileLayout tile_layout(int H, int W) {
     l.ntiles = l.gx * l.gy;
     const size_t n = (size_t)l.ntiles;
     size_t o = 0;
-    l.count = o; o += n * sizeof(uint32_t);
-    o = (o + 15) / 16 * 16;
-    l.counters = o; o = align_up(o + 4 * sizeof(uint32_t));   // count+counters are zeroed by one memset
+    l.count = o; o += n * SRF_TILE_CTR_STRIDE * sizeof(uint32_t);   // one 256 B block per tile
+    l.counters = o; o = align_up(o + 4 * sizeof(uint32_t));   // blocks+counters are zeroed by one memset
     l.ranges = o; o = align_up(o + n * sizeof(uint2));
-    l.cursor = o; o = align_up(o + n * sizeof(uint32_t));
     l.big = o; o = align_up(o + n * sizeof(uint32_t));
     l.total = o + 256;
     return l;
@@ -121,7 +119,7 @@ int srf_state_layout(int P, int H, int W, size_t geom_off[3], size_t tile_off[5]
     const TileLayout t = tile_layout(H, W);
     const ImageLayout i = image_layout(H, W);
     if (geom_off) { geom_off[0] = g.rec; geom_off[1] = g.depths; geom_off[2] = g.rects; }
-    if (tile_off) { tile_off[0] = t.count; tile_off[1] = t.counters; tile_off[2] = t.ranges; tile_off[3] = t.cursor; tile_off[4] = t.big; }
+    if (tile_off) { tile_off[0] = t.count; tile_off[1] = t.counters; tile_off[2] = t.ranges; tile_off[3] = t.count + sizeof(uint32_t); tile_off[4] = t.big; }
     if (image_off) { image_off[0] = i.accum; image_off[1] = i.ncontrib; }
     return 0;
 }
@@ -150,7 +148,6 @@ int srf_forward_preprocess(srf_stream_t stream_, int P, int D, int M,
     b.tile_count = at<uint32_t>(tile_state, tl.count);
     b.counters = at<uint32_t>(tile_state, tl.counters);
     b.ranges = at<uint2>(tile_state, tl.ranges);
-    b.cursor = at<uint32_t>(tile_state, tl.cursor);
     b.big_list = at<uint32_t>(tile_state, tl.big);
 
     if (P > 0) {
@@ -215,7 +212,6 @@ int srf_forward_render(srf_stream_t stream_, int P, int image_height, int image_
     b.tile_count = at<uint32_t>(tile_state, tl.count);
     b.counters = at<uint32_t>(tile_state, tl.counters);
     b.ranges = at<uint2>(tile_state, tl.ranges);
-    b.cursor = at<uint32_t>(tile_state, tl.cursor);
     b.big_list = at<uint32_t>(tile_state, tl.big);
     b.entries = static_cast<uint64_t*>(entries);
     b.point_list = point_list;

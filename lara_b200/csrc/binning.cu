@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     const int chunk = (a.ntiles + 1023) / 1024;
     const int begin = min(tid * chunk, a.ntiles), end = min(begin + chunk, a.ntiles);
     uint32_t local = 0;
-    for (int t = begin; t < end; ++t) local += a.tile_count[t];
+    for (int t = begin; t < end; ++t) local += a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -52,9 +52,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     __syncthreads();
     uint32_t running = s_warp[wid] + incl - local;
     for (int t = begin; t < end; ++t) {
-        const uint32_t c = a.tile_count[t];
+        const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
         a.ranges[t] = c ? make_uint2(running, running + c) : make_uint2(0u, 0u);
-        a.cursor[t] = running;
+        a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE + 1] = running;   // bucket cursor
         if (c > (uint32_t)kSmallCap) {
             const uint32_t slot = atomicAdd(&a.counters[1], 1u);
             a.big_list[slot] = (uint32_t)t;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
 }
 
 __device__ __forceinline__ void emit_instance(const BinArgs& a, int tile, uint64_t key) {
-    const uint32_t slot = atomicAdd(&a.cursor[tile], 1u);
+    const uint32_t slot = atomicAdd(&a.tile_count[(size_t)tile * SRF_TILE_CTR_STRIDE + 1], 1u);
     if (slot < a.capacity) a.entries[slot] = key;
 }
 
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) sort_small_kernel(BinArgs a) {
     const int tid = threadIdx.x;
     // rewind this tile's bucket cursor so that a re-run with a larger capacity (after an
     // optimistic-capacity overflow) can scatter again without repeating the scan
-    if (tid == 0) a.cursor[blockIdx.x] = r.x;
+    if (tid == 0) a.tile_count[(size_t)blockIdx.x * SRF_TILE_CTR_STRIDE + 1] = r.x;
     if (n <= 0 || n > kSmallCap || r.y > a.capacity) return;
     const uint64_t* src = a.entries + r.x;
     for (int i = tid; i < n; i += 256) s_keys[i] = src[i];

@@ -72,7 +72,7 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst, const float*
 // Adds one instance to every tile of rect [x0,x1) x [y0,y1).
 __device__ __forceinline__ void count_tiles_serial(uint32_t* tile_count, int gx, int x0, int y0, int x1, int y1) {
     for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[y * gx + x], 1u);
+        for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[(size_t)(y * gx + x) * SRF_TILE_CTR_STRIDE], 1u);
 }
 
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
@@ -238,13 +238,41 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 rgb[2] = __ldg(a.colors_precomp + (size_t)idx * 3 + 2);
             }
             const float opac = __ldg(a.opacities + idx);
+            // Conservative screen-space box of the pixels where this splat's alpha can reach
+            // 1/255 (the blend's skip threshold): alpha >= 1/255  =>  min(rho3d, rho2d) <= tau with
+            // tau = 2 ln(255 opacity).  rho2d <= tau is a disc around the AABB centre; rho3d <= tau
+            // is the projected ellipse u^2+v^2 <= tau whose exact bounds follow from the same
+            // quadratic form as the reference's AABB with diag(1,1,-1) replaced by diag(tau,tau,-1).
+            // Used only to skip work per warp; widened by a margin so it never changes a result.
+            float bx0, by0, bx1, by1;
+            if (opac < 0.00392156862745098f) {
+                bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;   // opacity*G < 1/255 for every G <= 1
+            } else {
+                const float tau = 2.0f * logf(opac * 255.0f) * 1.0001f + 1.0e-3f;
+                const float r2 = sqrtf(0.5f * tau);
+                bx0 = cxs - r2; bx1 = cxs + r2; by0 = cys - r2; by1 = cys + r2;
+                const float qw = tau * (Twx * Twx + Twy * Twy) - Twz * Twz;
+                if (qw < 0.0f) {
+                    const float iq = 1.0f / qw;
+                    const float ex_c = (tau * (Tux * Twx + Tuy * Twy) - Tuz * Twz) * iq;
+                    const float ey_c = (tau * (Tvx * Twx + Tvy * Twy) - Tvz * Twz) * iq;
+                    const float ex_h = sqrtf(fmaxf(0.0f, ex_c * ex_c - (tau * (Tux * Tux + Tuy * Tuy) - Tuz * Tuz) * iq));
+                    const float ey_h = sqrtf(fmaxf(0.0f, ey_c * ey_c - (tau * (Tvx * Tvx + Tvy * Tvy) - Tvz * Tvz) * iq));
+                    bx0 = fminf(bx0, ex_c - ex_h); bx1 = fmaxf(bx1, ex_c + ex_h);
+                    by0 = fminf(by0, ey_c - ey_h); by1 = fmaxf(by1, ey_c + ey_h);
+                    const float mx = 1.0f + 1.0e-3f * (bx1 - bx0), my = 1.0f + 1.0e-3f * (by1 - by0);
+                    bx0 -= mx; bx1 += mx; by0 -= my; by1 += my;
+                } else {
+                    bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;   // the tau-ellipse crosses the camera plane: unbounded
+                }
+            }
             float4* r = a.rec + (size_t)idx * SRF_REC_QUADS;
             r[0] = make_float4(Tux, Tuy, Tuz, Tvx);
             r[1] = make_float4(Tvy, Tvz, Twx, Twy);
             r[2] = make_float4(Twz, cxs, cys, opac);
             r[3] = make_float4(nx, ny, nz, pvz);
             r[4] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(clampbits));
-            r[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r[5] = make_float4(bx0, by0, bx1, by1);
             a.depths[idx] = pvz;
         } else {
             radius = 0; x0 = y0 = x1 = y1 = 0; ntiles = 0;
@@ -266,7 +294,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
         const int w = bx1 - bx0, n = w * (by1 - by0);
         for (int t = lane; t < n; t += 32) {
             const int ty = t / w, tx = t - ty * w;
-            atomicAdd(&a.tile_count[(by0 + ty) * a.gx + bx0 + tx], 1u);
+            atomicAdd(&a.tile_count[(size_t)((by0 + ty) * a.gx + bx0 + tx) * SRF_TILE_CTR_STRIDE], 1u);
         }
     }
 }

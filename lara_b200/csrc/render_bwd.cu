@@ -84,7 +84,7 @@ __device__ __forceinline__ void warp_reduce_scatter18(const float (&v)[18], int 
 }
 
 __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
-    __shared__ float4 s_rec[SRF_REC_QUADS - 1][256];
+    __shared__ float4 s_rec[SRF_REC_QUADS][256];
     __shared__ __align__(16) float s_grad[256 * SRF_GRAD_FLOATS];
     __shared__ uint32_t s_id[256];
     __shared__ int s_touched[256];
@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     const size_t npix = (size_t)a.W * a.H;
     const size_t pix = (size_t)pyi * a.W + pxi;
+    const float wxmin = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, wxmax = wxmin + 7.0f;
+    const float wymin = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f, wymax = wymin + 3.0f;
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
             s_id[tid] = id;
             const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
 #pragma unroll
-            for (int k = 0; k < SRF_REC_QUADS - 1; ++k) s_rec[k][tid] = ldg4(r + k);
+            for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][tid] = ldg4(r + k);
         }
         {
             float4* g4 = reinterpret_cast<float4*>(s_grad + tid * SRF_GRAD_FLOATS);
@@ -165,9 +167,24 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
         __syncthreads();
 
         const int cnt = min(256, n_eff - b * 256);
-        for (int j = 0; j < cnt; ++j) {
+        const int nchunks = (cnt + 31) >> 5;
+        for (int c = 0; c < nchunks; ++c) {
+          // warp-level cull, 32 splats per ballot: skip splats behind the warp's deepest
+          // contributor and splats whose alpha >= 1/255 box misses the warp's 8x4 pixel block
+          unsigned hits;
+          {
+            const int jt = (c << 5) + lane;
+            bool hit = false;
+            if (jt < cnt && n_eff - 1 - (b * 256 + jt) < wmax) {
+                const float4 cb = s_rec[5][jt];
+                hit = !(cb.x > wxmax || cb.z < wxmin || cb.y > wymax || cb.w < wymin);
+            }
+            hits = __ballot_sync(0xffffffffu, hit);
+          }
+          while (hits) {
+            const int j = (c << 5) + __ffs(hits) - 1;
+            hits &= hits - 1;
             const int pos = n_eff - 1 - (b * 256 + j);   // 0-based position in the tile list
-            if (pos >= wmax) continue;                    // warp-uniform
             bool contrib = inside && pos < last_contributor;
             PairEval e;
             const float4 q0 = s_rec[0][j], q1 = s_rec[1][j], q2 = s_rec[2][j];
@@ -275,6 +292,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
             warp_reduce_scatter18(g, lane, total, index);
             if (index >= 0) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + index], total);
             if (lane == 0) s_touched[j] = 1;
+          }
         }
         __syncthreads();
 

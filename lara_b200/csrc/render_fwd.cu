@@ -14,7 +14,7 @@
 namespace srf {
 
 __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
-    __shared__ float4 s_rec[SRF_REC_QUADS - 1][256];  // q0..q4 (q5 is not needed by the blend)
+    __shared__ float4 s_rec[SRF_REC_QUADS][256];
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
@@ -24,6 +24,10 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
+    // pixel-centre rectangle of this warp's 8x4 block, for the warp-level cull
+    const int lane = tid & 31, wid = tid >> 5;
+    const float wxmin = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, wxmax = wxmin + 7.0f;
+    const float wymin = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f, wymax = wymin + 3.0f;
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;  // overflowed optimistic capacity: host re-runs
@@ -47,14 +51,33 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             const uint32_t id = __ldg(a.point_list + range.x + progress);
             const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
 #pragma unroll
-            for (int k = 0; k < SRF_REC_QUADS - 1; ++k) s_rec[k][tid] = ldg4(r + k);
+            for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][tid] = ldg4(r + k);
         }
         __syncthreads();
         const int cnt = min(256, todo);
         // warp-uniform skip: a fully saturated warp only helps with staging
         if (__all_sync(0xffffffffu, done)) continue;
-        for (int j = 0; !done && j < cnt; ++j) {
-            contributor++;
+        const int nchunks = (cnt + 31) >> 5;
+        for (int c = 0; c < nchunks; ++c) {
+          // 32 splats per step: lane l tests splat c*32+l against the warp's pixel block; the
+          // surviving splats are then visited in list order.  Skipped splats cannot reach
+          // alpha >= 1/255 anywhere in the block, so no pixel's result changes.
+          unsigned hits;
+          {
+            const int jt = (c << 5) + lane;
+            bool hit = false;
+            if (jt < cnt) {
+                const float4 cb = s_rec[5][jt];
+                hit = !(cb.x > wxmax || cb.z < wxmin || cb.y > wymax || cb.w < wymin);
+            }
+            hits = __ballot_sync(0xffffffffu, hit);
+          }
+          if (__all_sync(0xffffffffu, done)) break;
+          while (hits) {
+            const int j = (c << 5) + __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (done) continue;
+            contributor = (uint32_t)(b * 256 + j + 1);
             PairEval e;
             eval_pair(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
             if (!e.valid) continue;
@@ -88,6 +111,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             C2 = fma_(T, fmul_(alpha, q4.z), C2);
             T = test_T;
             last_contributor = contributor;
+          }
         }
     }
 

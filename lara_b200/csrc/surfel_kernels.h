@@ -27,7 +27,7 @@ struct PreprocessArgs {
     float4* rec;                 // [P*6] out
     float* depths;               // [P] out
     uint2* rects;                // [P] out: (x0 | y0<<16, x1 | y1<<16)
-    uint32_t* tile_count;        // [ntiles] in/out (zeroed by the caller)
+    uint32_t* tile_count;        // [ntiles * SRF_TILE_CTR_STRIDE] in/out (zeroed by the caller)
 };
 
 struct BinArgs {
@@ -37,9 +37,8 @@ struct BinArgs {
     uint32_t capacity;           // number of instance slots in entries / point_list
     const float* depths;
     const uint2* rects;          // empty rect = culled
-    uint32_t* tile_count;        // [ntiles]
+    uint32_t* tile_count;        // [ntiles * SRF_TILE_CTR_STRIDE]: word 0 count, word 1 bucket cursor
     uint2* ranges;               // [ntiles] out
-    uint32_t* cursor;            // [ntiles] scratch
     uint32_t* counters;          // [4]: num_rendered, big_count, overflow, spare
     uint32_t* big_list;          // [ntiles] scratch
     uint64_t* entries;           // [capacity] scratch: depth_bits<<32 | gaussian idx, bucketed by tile

@@ -37,7 +37,7 @@ def unpack_state(state: ForwardState, P: int, H: int, W: int) -> Dict[str, torch
         out["rect"] = torch.stack([rects[:, 0] & 0xFFFF, (rects[:, 0] >> 16) & 0xFFFF,
                                    rects[:, 1] & 0xFFFF, (rects[:, 1] >> 16) & 0xFFFF], dim=1)
         out["tiles_touched"] = (out["rect"][:, 2] - out["rect"][:, 0]) * (out["rect"][:, 3] - out["rect"][:, 1])
-    out["tile_count"] = state.tile[t_off[0]:t_off[0] + 4 * ntiles].view(torch.int32)
+    out["tile_count"] = state.tile[t_off[0]:t_off[0] + 256 * ntiles].view(torch.int32).view(ntiles, 64)[:, 0]
     out["counters"] = state.tile[t_off[1]:t_off[1] + 16].view(torch.int32)
     out["ranges"] = state.tile[t_off[2]:t_off[2] + 8 * ntiles].view(torch.int32).view(ntiles, 2)
     out["accum"] = state.image[i_off[0]:i_off[0] + 12 * npix].view(torch.float32).view(3, H, W)
