@@ -122,6 +122,16 @@ int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat);
 
+/* ---- optional per-kernel timing (no reference counterpart; used by bench.py's roofline) --
+ * Between srf_profile_begin() and srf_profile_end() every kernel launch made by this
+ * library is bracketed by CUDA events on its launching stream.  srf_profile_end waits for
+ * them and returns, per kernel id, the summed device time in ms and the launch count.
+ * Kernel ids: 0 preprocess_fwd, 1 tile_scan, 2 scatter, 3 sort_small, 4 sort_big,
+ * 5 render_fwd, 6 render_bwd, 7 preprocess_bwd (SRF_NUM_KERNELS entries).  Not thread-safe. */
+#define SRF_NUM_KERNELS 8
+int srf_profile_begin(void);
+int srf_profile_end(float* ms_out, int* launches_out, int n);
+
 /* ---- markVisible (DSR/rasterize_points.cu:242-261, rasterizer_impl.cu:141-153) ----
  * present[i] = 1 iff the view-space z of means3D[i] is > 0.2 (one byte per Gaussian). */
 int srf_mark_visible(srf_stream_t stream, int P, const float* means3D,

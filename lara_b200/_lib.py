@@ -57,6 +57,8 @@ SIGNATURES = {
         _P, _P, _P, _P,                          # dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat
     ]),
     "srf_mark_visible": (c_int, [_P, c_int, _P, _P, _P, _P]),
+    "srf_profile_begin": (c_int, []),
+    "srf_profile_end": (c_int, [POINTER(c_float), POINTER(c_int), c_int]),
 }
 
 _lib = None
@@ -119,3 +121,22 @@ def layout(lib, P: int, H: int, W: int):
     i = (c_size_t * 2)()
     check(lib.srf_state_layout(P, H, W, g, t, i), lib)
     return list(g), list(t), list(i)
+
+
+KERNEL_NAMES = ["preprocess_fwd", "tile_scan", "scatter", "sort_small", "sort_big", "render_fwd",
+                "render_bwd", "preprocess_bwd"]
+
+
+def profile_begin(lib=None) -> None:
+    l = lib or load()
+    check(l.srf_profile_begin(), l)
+
+
+def profile_end(lib=None):
+    """Returns {kernel name: (total ms, launches)} for the launches since profile_begin()."""
+    l = lib or load()
+    n = len(KERNEL_NAMES)
+    ms = (c_float * n)()
+    cnt = (c_int * n)()
+    check(l.srf_profile_end(ms, cnt, n), l)
+    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

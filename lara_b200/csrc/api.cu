@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/surfel_rasterizer.h"
 #include "surfel_common.cuh"
 #include "surfel_kernels.h"
@@ -75,11 +77,64 @@ T* at(const void* base, size_t off) {
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 255) != 0; }
 
+// ---- optional per-kernel timing --------------------------------------------------
+struct ProfSpan { int kernel; cudaEvent_t start, stop; };
+bool g_prof_on = false;
+std::vector<ProfSpan> g_spans;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t g_open[srf::K_COUNT];
+
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
 }  // namespace
+
+namespace srf {
+void prof_start(int kernel, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    g_open[kernel] = take_event();
+    cudaEventRecord(g_open[kernel], stream);
+}
+void prof_stop(int kernel, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfSpan s; s.kernel = kernel; s.start = g_open[kernel]; s.stop = take_event();
+    cudaEventRecord(s.stop, stream);
+    g_spans.push_back(s);
+}
+}  // namespace srf
 
 extern "C" {
 
 int srf_abi_version(void) { return SRF_ABI_VERSION; }
+
+int srf_profile_begin(void) {
+    for (auto& s : g_spans) { g_event_pool.push_back(s.start); g_event_pool.push_back(s.stop); }
+    g_spans.clear();
+    g_prof_on = true;
+    return 0;
+}
+
+int srf_profile_end(float* ms_out, int* launches_out, int n) {
+    g_prof_on = false;
+    if (n < srf::K_COUNT || !ms_out || !launches_out) return fail("srf_profile_end: need arrays of %d entries", (int)srf::K_COUNT);
+    for (int k = 0; k < n; ++k) { ms_out[k] = 0.f; launches_out[k] = 0; }
+    for (auto& s : g_spans) {
+        cudaError_t e = cudaEventSynchronize(s.stop);
+        if (e != cudaSuccess) return cuda_fail("profile event sync", e);
+        float ms = 0.f;
+        e = cudaEventElapsedTime(&ms, s.start, s.stop);
+        if (e != cudaSuccess) return cuda_fail("profile elapsed", e);
+        ms_out[s.kernel] += ms;
+        launches_out[s.kernel] += 1;
+        g_event_pool.push_back(s.start); g_event_pool.push_back(s.stop);
+    }
+    g_spans.clear();
+    return 0;
+}
 const char* srf_last_error(void) { return g_err; }
 
 int srf_geom_state_bytes(int P, size_t* bytes) {

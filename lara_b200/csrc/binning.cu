@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(1024) sort_big_kernel(BinArgs a) {
 }
 
 cudaError_t launch_tile_scan(const BinArgs& a, cudaStream_t stream) {
+    prof_start(K_TILE_SCAN, stream);
     tile_scan_kernel<<<1, 1024, 0, stream>>>(a);
+    prof_stop(K_TILE_SCAN, stream);
     return cudaGetLastError();
 }
 
@@ -191,12 +193,22 @@ cudaError_t launch_bin_and_sort(const BinArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     if (a.P <= 0) return cudaSuccess;
+    prof_start(K_SCATTER, stream);
     scatter_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+    prof_stop(K_SCATTER, stream);
+    prof_start(K_SORT_SMALL, stream);
     sort_small_kernel<<<a.ntiles, 256, 0, stream>>>(a);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    prof_stop(K_SORT_SMALL, stream);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    prof_start(K_SORT_BIG, stream);
     sort_big_kernel<<<sms, 1024, big_smem, stream>>>(a);
+    prof_stop(K_SORT_BIG, stream);
     return cudaGetLastError();
 }
 

@@ -326,7 +326,9 @@ cudaError_t launch_preprocess_fwd(const PreprocessArgs& a, cudaStream_t stream) 
                         ? 1 : 0;
     const size_t dyn = args.stage_sh ? sh_bytes : 0;
     const int grid = (a.P + 255) / 256;
+    prof_start(K_PREPROCESS_FWD, stream);
     preprocess_fwd_kernel<<<grid, 256, dyn, stream>>>(args);
+    prof_stop(K_PREPROCESS_FWD, stream);
     return cudaGetLastError();
 }
 

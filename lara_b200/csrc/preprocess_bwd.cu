@@ -250,10 +250,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t stream) {
     if (a.P <= 0) return cudaSuccess;
     const int grid = (a.P + 255) / 256;
+    prof_start(K_PREPROCESS_BWD, stream);
     if (a.accumulate)
         preprocess_bwd_kernel<true><<<grid, 256, 0, stream>>>(a);
     else
         preprocess_bwd_kernel<false><<<grid, 256, 0, stream>>>(a);
+    prof_stop(K_PREPROCESS_BWD, stream);
     return cudaGetLastError();
 }
 

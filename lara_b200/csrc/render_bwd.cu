@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
 cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
     if (ntiles <= 0) return cudaSuccess;
+    prof_start(K_RENDER_BWD, stream);
     render_bwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    prof_stop(K_RENDER_BWD, stream);
     return cudaGetLastError();
 }
 

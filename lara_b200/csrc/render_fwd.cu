@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
 cudaError_t launch_render_fwd(const RenderFwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
     if (ntiles <= 0) return cudaSuccess;
+    prof_start(K_RENDER_FWD, stream);
     render_fwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    prof_stop(K_RENDER_FWD, stream);
     return cudaGetLastError();
 }
 

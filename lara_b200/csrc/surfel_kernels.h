@@ -98,6 +98,12 @@ struct PreprocessBwdArgs {
     float* dL_dtransMat;         // [P,9] or null
 };
 
+// Optional per-kernel CUDA-event timing (srf_profile_begin/end in the C ABI); no-ops unless enabled.
+enum KernelId { K_PREPROCESS_FWD = 0, K_TILE_SCAN, K_SCATTER, K_SORT_SMALL, K_SORT_BIG, K_RENDER_FWD,
+                K_RENDER_BWD, K_PREPROCESS_BWD, K_COUNT };
+void prof_start(int kernel, cudaStream_t stream);
+void prof_stop(int kernel, cudaStream_t stream);
+
 cudaError_t launch_preprocess_fwd(const PreprocessArgs& a, cudaStream_t stream);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                                 cudaStream_t stream);

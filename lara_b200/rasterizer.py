@@ -187,7 +187,7 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tran
 
 def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scales, rotations,
                  transMat_precomp, raster_settings, grad_color, grad_allmap, *,
-                 out: Optional[dict] = None, accumulate: bool = False):
+                 out: Optional[dict] = None, accumulate: bool = False, need_means2D: bool = True):
     """Enqueue one backward; returns a dict of gradient tensors.
 
     ``out`` may supply pre-allocated (possibly strided-into-a-flat-buffer but contiguous)
@@ -211,7 +211,7 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
 
     g = {
         "means3D": get("means3D", (P, 3)),
-        "means2D": get("means2D", (P, 3)),
+        "means2D": get("means2D", (P, 3)) if need_means2D else None,
         "sh": get("sh", (P, M, 3)) if shs is not None else None,
         "colors_precomp": get("colors_precomp", (P, 3)) if colors_precomp is not None else None,
         "opacities": get("opacities", (P, 1)),

@@ -1,0 +1,80 @@
+"""Size-independent properties at BASELINE.json's full sizes (no oracle needed): determinism,
+sortedness, conservation of instance counts, linearity of the backward, view-sharded
+accumulation equals the sum of per-view gradients."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, run_candidate, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big(cuda_device):
+    from lara_b200 import scene as S
+    sc = S.scene(131072, 0)
+    cams = S.cameras(4, 512, 512, 0)
+    return sc, cams
+
+
+def test_forward_is_deterministic_and_lists_are_consistent(cuda_device, big):
+    sc, cams = big
+    a = run_candidate(sc, cams[0], torch.ones(3), cuda_device)
+    b = run_candidate(sc, cams[0], torch.ones(3), cuda_device)
+    for k in ("color", "allmap", "point_list", "ranges", "n_contrib", "radii"):
+        assert np.array_equal(a[k], b[k]), k
+    R = a["num_rendered"]
+    assert R == int(a["tiles_touched"].sum()) == int((a["ranges"][:, 1] - a["ranges"][:, 0]).sum())
+    ne = a["ranges"][a["ranges"][:, 1] > a["ranges"][:, 0]]
+    order = np.argsort(ne[:, 0])
+    assert ne[order][0, 0] == 0 and ne[order][-1, 1] == R and np.array_equal(ne[order][1:, 0], ne[order][:-1, 1])
+    d = a["depths"][a["point_list"]]
+    for s, e in ne[:: max(1, len(ne) // 64)]:
+        assert np.all(np.diff(d[s:e]) >= 0)
+    assert np.all(a["n_contrib"][0].reshape(32, 16, 32, 16).transpose(0, 2, 1, 3).reshape(1024, 256).max(1)
+                  <= (a["ranges"][:, 1] - a["ranges"][:, 0]))
+    alpha = a["allmap"][1]
+    assert alpha.min() >= 0.0 and alpha.max() <= 1.0 and np.allclose(1.0 - alpha, a["accum"][0], atol=1e-6)
+
+
+def test_backward_is_linear_in_upstream_gradients(cuda_device, big):
+    from lara_b200 import scene as S
+    sc, cams = big
+    gc, ga = S.upstream_grads(512, 512, 3)
+    g1 = run_candidate(sc, cams[1], torch.ones(3), cuda_device, grads=(gc, ga))
+    g2 = run_candidate(sc, cams[1], torch.ones(3), cuda_device, grads=(2.0 * gc, 2.0 * ga))
+    g0 = run_candidate(sc, cams[1], torch.ones(3), cuda_device, grads=(0.0 * gc, 0.0 * ga))
+    for k in ("g_means3D", "g_sh", "g_opacities", "g_scales", "g_rotations", "g_means2D"):
+        assert np.isfinite(g1[k]).all()
+        assert rel_err(g2[k], 2.0 * g1[k]) < 1e-5, k
+        assert float(np.abs(g0[k]).max()) == 0.0, k
+
+
+def test_view_sharded_accumulation_equals_sum_of_views(cuda_device, big):
+    from lara_b200 import rasterizer as R, scene as S, sharded
+    sc, cams = big
+    dev = cuda_device
+    params = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    sets = [S.settings_for(c, torch.ones(3), 1, dev, R.GaussianRasterizationSettings) for c in cams]
+    ups = [tuple(t.to(dev) for t in S.upstream_grads(512, 512, i)) for i in range(len(cams))]
+    outs, grads = sharded.render_views(params, sets, lambda vid, c, a: ups[vid])
+    torch.cuda.synchronize()
+    acc = {k: np.zeros(v.shape, np.float64) for k, v in grads.views.items()}
+    for i, c in enumerate(cams):
+        g = run_candidate(sc, c, torch.ones(3), dev, grads=ups[i])
+        for k in acc:
+            acc[k] += g["g_" + k]
+    for k in acc:
+        assert rel_err(grads.views[k].cpu().numpy(), acc[k]) < 1e-5, k
+
+
+def test_lara_sized_scene_runs(cuda_device):
+    """LaRa's own size: 524 288 Gaussians at 512^2: sanity + no NaNs."""
+    from lara_b200 import scene as S
+    sc = S.scene(524288, 1)
+    cam = S.cameras(1, 512, 512, 1)[0]
+    out = run_candidate(sc, cam, torch.zeros(3), cuda_device, grads=S.upstream_grads(512, 512, 0, lara_like=True))
+    assert out["num_rendered"] > 524288
+    for k in ("color", "allmap", "g_means3D", "g_sh", "g_opacities", "g_scales", "g_rotations"):
+        assert np.isfinite(out[k]).all(), k
