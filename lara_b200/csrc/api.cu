@@ -31,7 +31,7 @@ int cuda_fail(const char* what, cudaError_t e) {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct GeomLayout { size_t rec, depths, rects, total; };
-struct TileLayout { size_t count, counters, ranges, big, total; int gx, gy, ntiles; };
+struct TileLayout { size_t count, counters, ranges, big, order, total; int gx, gy, ntiles; };
 struct ImageLayout { size_t accum, ncontrib, total; };
 
 GeomLayout geom_layout(int P) {
@@ -56,6 +56,7 @@ TileLayout tile_layout(int H, int W) {
     l.counters = o; o = align_up(o + 4 * sizeof(uint32_t));   // blocks+counters are zeroed by one memset
     l.ranges = o; o = align_up(o + n * sizeof(uint2));
     l.big = o; o = align_up(o + n * sizeof(uint32_t));
+    l.order = o; o = align_up(o + n * sizeof(uint32_t));
     l.total = o + 256;
     return l;
 }
@@ -204,6 +205,7 @@ int srf_forward_preprocess(srf_stream_t stream_, int P, int D, int M,
     b.counters = at<uint32_t>(tile_state, tl.counters);
     b.ranges = at<uint2>(tile_state, tl.ranges);
     b.big_list = at<uint32_t>(tile_state, tl.big);
+    b.tile_order = at<uint32_t>(tile_state, tl.order);
 
     if (P > 0) {
         if (!means3D || !opacities || !viewmatrix || !campos || !radii)
@@ -268,6 +270,7 @@ int srf_forward_render(srf_stream_t stream_, int P, int image_height, int image_
     b.counters = at<uint32_t>(tile_state, tl.counters);
     b.ranges = at<uint2>(tile_state, tl.ranges);
     b.big_list = at<uint32_t>(tile_state, tl.big);
+    b.tile_order = at<uint32_t>(tile_state, tl.order);
     b.entries = static_cast<uint64_t*>(entries);
     b.point_list = point_list;
     cudaError_t e;
@@ -284,6 +287,7 @@ int srf_forward_render(srf_stream_t stream_, int P, int image_height, int image_
     r.W = image_width; r.H = image_height; r.gx = tl.gx; r.gy = tl.gy;
     r.capacity = (uint32_t)capacity;
     r.ranges = b.ranges;
+    r.tile_order = b.tile_order;
     r.point_list = point_list;
     r.rec = P > 0 ? at<float4>(geom_state, gl.rec) : nullptr;
     r.bg = background;
@@ -331,6 +335,7 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
     r.W = image_width; r.H = image_height; r.gx = tl.gx; r.gy = tl.gy;
     r.capacity = (uint32_t)capacity;
     r.ranges = at<uint2>(tile_state, tl.ranges);
+    r.tile_order = at<uint32_t>(tile_state, tl.order);
     r.point_list = point_list;
     r.rec = at<float4>(geom_state, gl.rec);
     r.bg = background;

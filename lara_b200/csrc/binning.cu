@@ -23,6 +23,72 @@ namespace srf {
 constexpr int kSmallCap = 2048;   // entries sorted by the 256-thread per-tile kernel (16 KB smem)
 constexpr int kBigCap = 16384;    // entries sorted in smem by the 1024-thread persistent kernel (128 KB)
 
+// Ascending bitonic network over data[0..n) (n arbitrary; indices >= n act as +inf and
+// are never touched).  All compare-exchanges are ascending ("normalised" network), so
+// padding needs no storage.  Works on shared or global memory; the CTA must call it
+// convergently.
+template <typename Ptr>
+__device__ __forceinline__ void bitonic_sort_cta(Ptr data, int n, int tid, int nthreads) {
+    if (n < 2) return;
+    int m = 1;
+    while (m < n) m <<= 1;
+    const int npairs = m >> 1;
+    for (int k = 2, lk = 1; k <= m; k <<= 1, ++lk) {
+        const int hk = k >> 1;
+        for (int i = tid; i < npairs; i += nthreads) {
+            const int blk = i >> (lk - 1), off = i & (hk - 1);
+            const int lo = (blk << lk) + off, hi = (blk << lk) + k - 1 - off;
+            if (hi < n) {
+                const uint64_t x = data[lo], y = data[hi];
+                if (x > y) { data[lo] = y; data[hi] = x; }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = tid; i < npairs; i += nthreads) {
+                const int lo = 2 * i - (i & (j - 1)), hi = lo + j;
+                if (hi < n) {
+                    const uint64_t x = data[lo], y = data[hi];
+                    if (x > y) { data[lo] = y; data[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Shared-memory variant for a 256-thread CTA: the array is padded with +inf up to the next
+// power of two so the inner loops carry no bounds checks, every thread owns a fixed set of
+// pairs per stage, and index arithmetic is shifts/masks only.
+__device__ __forceinline__ void bitonic_sort_smem256(uint64_t* data, int n, int tid) {
+    if (n < 2) return;
+    int m = 2, lm = 1;
+    while (m < n) { m <<= 1; ++lm; }
+    for (int i = n + tid; i < m; i += 256) data[i] = ~0ull;
+    __syncthreads();
+    const int npairs = m >> 1;
+    for (int k = 2, lk = 1; k <= m; k <<= 1, ++lk) {
+        const int hk = k >> 1;
+#pragma unroll 4
+        for (int i = tid; i < npairs; i += 256) {
+            const int base = (i >> (lk - 1)) << lk, off = i & (hk - 1);
+            const int lo = base + off, hi = base + k - 1 - off;
+            const uint64_t x = data[lo], y = data[hi];
+            if (x > y) { data[lo] = y; data[hi] = x; }
+        }
+        __syncthreads();
+        for (int j = hk >> 1; j > 0; j >>= 1) {
+#pragma unroll 4
+            for (int i = tid; i < npairs; i += 256) {
+                const int lo = 2 * i - (i & (j - 1)), hi = lo + j;
+                const uint64_t x = data[lo], y = data[hi];
+                if (x > y) { data[lo] = y; data[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     __shared__ uint32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -60,6 +126,47 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
             a.big_list[slot] = (uint32_t)t;
         }
         running += c;
+    }
+    // Longest-processing-time-first launch order for the per-tile blend CTAs: the grid is only
+    // a few waves deep and per-tile work varies by >10x, so scheduling the heavy tiles first
+    // removes most of the tail.  A 64-bucket counting sort on the instance count is enough.
+    {
+        __shared__ uint32_t s_bucket[64];
+        __shared__ uint32_t s_max;
+        if (tid < 64) s_bucket[tid] = 0;
+        if (tid == 0) s_max = 0;
+        __syncthreads();
+        uint32_t lmax = 0;
+        for (int t = tid; t < a.ntiles; t += 1024) lmax = max(lmax, a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) atomicMax(&s_max, lmax);
+        __syncthreads();
+        const uint32_t cmax = s_max + 1;
+        for (int t = tid; t < a.ntiles; t += 1024) {
+            const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+            const uint32_t bkt = 63u - (uint32_t)(((uint64_t)c * 64u) / cmax);   // heavy tiles -> low buckets
+            atomicAdd(&s_bucket[bkt], 1u);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            // exclusive scan of the 64 bucket sizes (two values per lane)
+            const uint32_t v0 = s_bucket[2 * lane], v1 = s_bucket[2 * lane + 1];
+            uint32_t sum = v0 + v1, inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            s_bucket[2 * lane] = inc - sum;
+            s_bucket[2 * lane + 1] = inc - sum + v0;
+        }
+        __syncthreads();
+        for (int t = tid; t < a.ntiles; t += 1024) {
+            const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+            const uint32_t bkt = 63u - (uint32_t)(((uint64_t)c * 64u) / cmax);
+            a.tile_order[atomicAdd(&s_bucket[bkt], 1u)] = (uint32_t)t;
+        }
     }
 }
 
@@ -99,40 +206,6 @@ __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
     }
 }
 
-// Ascending bitonic network over data[0..n) (n arbitrary; indices >= n act as +inf and
-// are never touched).  All compare-exchanges are ascending ("normalised" network), so
-// padding needs no storage.  Works on shared or global memory; the CTA must call it
-// convergently.
-template <typename Ptr>
-__device__ __forceinline__ void bitonic_sort_cta(Ptr data, int n, int tid, int nthreads) {
-    if (n < 2) return;
-    int m = 1;
-    while (m < n) m <<= 1;
-    const int npairs = m >> 1;
-    for (int k = 2; k <= m; k <<= 1) {
-        const int hk = k >> 1;
-        for (int i = tid; i < npairs; i += nthreads) {
-            const int blk = i / hk, off = i - blk * hk;
-            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
-            if (hi < n) {
-                const uint64_t x = data[lo], y = data[hi];
-                if (x > y) { data[lo] = y; data[hi] = x; }
-            }
-        }
-        __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = tid; i < npairs; i += nthreads) {
-                const int lo = 2 * i - (i & (j - 1)), hi = lo + j;
-                if (hi < n) {
-                    const uint64_t x = data[lo], y = data[hi];
-                    if (x > y) { data[lo] = y; data[hi] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) sort_small_kernel(BinArgs a) {
     __shared__ uint64_t s_keys[kSmallCap];
     const uint2 r = a.ranges[blockIdx.x];
@@ -145,7 +218,7 @@ __global__ void __launch_bounds__(256) sort_small_kernel(BinArgs a) {
     const uint64_t* src = a.entries + r.x;
     for (int i = tid; i < n; i += 256) s_keys[i] = src[i];
     __syncthreads();
-    bitonic_sort_cta(s_keys, n, tid, 256);
+    bitonic_sort_smem256(s_keys, n, tid);
     uint32_t* dst = a.point_list + r.x;
     for (int i = tid; i < n; i += 256) dst[i] = (uint32_t)s_keys[i];
 }

@@ -24,34 +24,47 @@ __device__ const float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0
                                     0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
                                     -0.5900435899266435f};
 
-// SH -> RGB (reference forward.cu:20-71).  `sh` points at this Gaussian's M x 3 block.
-__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh, float dirx, float diry,
-                                          float dirz, float rgb[3]) {
-    const float inv_len = 1.0f;  // caller passes normalised dir
-    (void)inv_len;
-    const float x = dirx, y = diry, z = dirz;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float r = kSH_C0 * sh[c];
-        if (deg > 0) {
-            r = r - kSH_C1 * y * sh[3 + c] + kSH_C1 * z * sh[6 + c] - kSH_C1 * x * sh[9 + c];
-            if (deg > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                r = r + kSH_C2[0] * xy * sh[12 + c] + kSH_C2[1] * yz * sh[15 + c] +
-                    kSH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + kSH_C2[3] * xz * sh[21 + c] +
-                    kSH_C2[4] * (xx - yy) * sh[24 + c];
-                if (deg > 2) {
-                    r = r + kSH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + kSH_C3[1] * xy * z * sh[30 + c] +
-                        kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                        kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                        kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] +
-                        kSH_C3[5] * z * (xx - yy) * sh[42 + c] + kSH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
-                }
+// SH -> RGB (reference forward.cu:20-71), written in the exact fp32 operation order of the
+// reference build (sm_100 SASS of computeColorFromSH: every term is fma(coef, sh[k], acc) with
+// coef = (C * basis) evaluated as below), so the colour is bit-identical too.
+// `sh` points at this Gaussian's M x 3 block, (x,y,z) is the normalised view direction.
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh, float x, float y, float z,
+                                          float rgb[3]) {
+    float r0 = fmul_(sh[0], kSH_C0), r1 = fmul_(sh[1], kSH_C0), r2 = fmul_(sh[2], kSH_C0);
+#define SRF_SH_ACC(coef, k)                       \
+    r0 = fma_((coef), sh[3 * (k) + 0], r0);       \
+    r1 = fma_((coef), sh[3 * (k) + 1], r1);       \
+    r2 = fma_((coef), sh[3 * (k) + 2], r2);
+    if (deg > 0) {
+        const float c1 = -fmul_(y, kSH_C1), c2 = fmul_(z, kSH_C1), c3 = -fmul_(x, kSH_C1);
+        SRF_SH_ACC(c1, 1) SRF_SH_ACC(c2, 2) SRF_SH_ACC(c3, 3)
+        if (deg > 1) {
+            const float xy = fmul_(y, x), yz = fmul_(z, y), xz = fmul_(z, x);
+            const float xx = fmul_(x, x), yy = fmul_(y, y), zz = fmul_(z, z);
+            const float zz2 = fadd_(zz, zz);
+            const float c4 = fmul_(xy, kSH_C2[0]);
+            const float c5 = fmul_(yz, kSH_C2[1]);
+            const float c6 = fmul_(fadd_(fadd_(zz2, -xx), -yy), kSH_C2[2]);
+            const float c7 = fmul_(xz, kSH_C2[3]);
+            const float xx_yy = fadd_(xx, -yy);
+            const float c8 = fmul_(xx_yy, kSH_C2[4]);
+            SRF_SH_ACC(c4, 4) SRF_SH_ACC(c5, 5) SRF_SH_ACC(c6, 6) SRF_SH_ACC(c7, 7) SRF_SH_ACC(c8, 8)
+            if (deg > 2) {
+                const float c9 = fmul_(fmul_(y, kSH_C3[0]), fma_(xx, 3.0f, -yy));
+                const float c10 = fmul_(fmul_(xy, kSH_C3[1]), z);
+                const float q = fadd_(fma_(zz, 4.0f, -xx), -yy);            // 4zz - xx - yy
+                const float c11 = fmul_(fmul_(y, kSH_C3[2]), q);
+                const float c12 = fmul_(fmul_(z, kSH_C3[3]), fma_(yy, -3.0f, fma_(xx, -3.0f, zz2)));
+                const float c13 = fmul_(q, fmul_(x, kSH_C3[4]));
+                const float c14 = fmul_(xx_yy, fmul_(z, kSH_C3[5]));
+                const float c15 = fmul_(fmul_(x, kSH_C3[6]), fma_(yy, -3.0f, xx));
+                SRF_SH_ACC(c9, 9) SRF_SH_ACC(c10, 10) SRF_SH_ACC(c11, 11) SRF_SH_ACC(c12, 12)
+                SRF_SH_ACC(c13, 13) SRF_SH_ACC(c14, 14) SRF_SH_ACC(c15, 15)
             }
         }
-        rgb[c] = r + 0.5f;
     }
+#undef SRF_SH_ACC
+    rgb[0] = fadd_(r0, 0.5f); rgb[1] = fadd_(r1, 0.5f); rgb[2] = fadd_(r2, 0.5f);
 }
 
 // Cooperative, 128-bit staging of `rows` consecutive rows of `row_floats` floats each
@@ -219,9 +232,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
             float rgb[3];
             int clampbits = 0;
             if (use_sh) {
-                float dx = px - s_cam[0], dy = py - s_cam[1], dz = pz - s_cam[2];
-                const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-                dx = dx / len; dy = dy / len; dz = dz / len;
+                float dx = fadd_(px, -s_cam[0]), dy = fadd_(py, -s_cam[1]), dz = fadd_(pz, -s_cam[2]);
+                const float len = __fsqrt_rn(fma_(dz, dz, fma_(dx, dx, fmul_(dy, dy))));
+                dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
                 if (a.stage_sh) {
                     sh_to_rgb(a.D, s_sh + tid * sh_row, dx, dy, dz, rgb);
                 } else {

@@ -83,7 +83,7 @@ __device__ __forceinline__ void warp_reduce_scatter18(const float (&v)[18], int 
     index = size > 0 ? base : -1;
 }
 
-__global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
     __shared__ float4 s_rec[SRF_REC_QUADS][256];
     __shared__ __align__(16) float s_grad[256 * SRF_GRAD_FLOATS];
     __shared__ uint32_t s_id[256];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
     __shared__ int s_wmax[8];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int tile = blockIdx.x;
+    const int tile = (int)a.tile_order[blockIdx.x];
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
     tile_pixel(tid, lx, ly);
@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
                 const float Twx = q1.z, Twy = q1.w;
                 const float opac = q2.w;
 
-                T = T / (1.0f - alpha);
+                // one reciprocal serves T / (1-alpha) and the background term's T_final / (1-alpha)
+                const float r1ma = __frcp_rn(1.0f - alpha);
+                T = T * r1ma;
                 const float w = alpha * T;  // dchannel_dcolor
                 float dL_dalpha = 0.0f;
                 // colour (backward.cu:331-346)
@@ -220,10 +222,13 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
                 g[SRF_G_DCOLOR + 2] = w * dpix2;
 
                 float dL_dz = 0.0f, dL_dweight = 0.0f;
-                // distortion / median terms (backward.cu:350-368); double constants as the reference
-                const double cd = (double)c_d;
-                const float m_d = (float)((100.0 * cd - 100.0 * 0.2) / ((100.0 - 0.2) * cd));
-                const float dmd_dd = (float)((100.0 * 0.2) / ((100.0 - 0.2) * cd * cd));
+                // distortion / median terms (backward.cu:350-368).  m_d = (FAR d - FAR NEAR)/((FAR-NEAR) d)
+                // = c1 - c2/d and d m_d/dd = c2/d^2; the reference evaluates both in double.  fp32 is
+                // enough here: the weight term below is stationary in m_d (its derivative is
+                // 2 (m_d A - D) ~ 0), and the gradients carry 1e-6 atomic-order noise anyway.
+                const float rcd = __frcp_rn(c_d);
+                const float m_d = fmaf(-(float)(20.0 / 99.8), rcd, (float)(100.0 / 99.8));
+                const float dmd_dd = (float)(20.0 / 99.8) * rcd * rcd;
                 if (pos == median_contributor - 1) {
                     dL_dz += dL_dmedian_depth;
                     dL_dweight += dL_dmax_dweight;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
                 dL_dalpha *= T;
                 last_alpha = alpha;
                 // background term (backward.cu:391-396)
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
 
                 const float dL_dG = opac * dL_dalpha;
                 dL_dz += w * dL_ddepth;
@@ -261,8 +266,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs a) {
                     // ray-splat branch: vjp through s = p.xy / p.z, p = k x l (backward.cu:405-435)
                     const float dL_dsx = dL_dG * -G * e.sx + dL_dz * Twx;
                     const float dL_dsy = dL_dG * -G * e.sy + dL_dz * Twy;
-                    const float dsx_pz = dL_dsx / e.pz;
-                    const float dsy_pz = dL_dsy / e.pz;
+                    const float rpz = __frcp_rn(e.pz);
+                    const float dsx_pz = dL_dsx * rpz;
+                    const float dsy_pz = dL_dsy * rpz;
                     const float dpx = dsx_pz, dpy = dsy_pz, dpz = -(dsx_pz * e.sx + dsy_pz * e.sy);
                     // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
                     const float dkx = e.ly * dpz - e.lz * dpy;

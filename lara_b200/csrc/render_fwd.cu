@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     __shared__ float4 s_rec[SRF_REC_QUADS][256];
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int tile = (int)a.tile_order[blockIdx.x];
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
     tile_pixel(tid, lx, ly);
@@ -40,7 +40,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float D = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
     float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
-    float median_depth = 0.f, median_weight = 0.f, median_contributor = -1.0f;
+    float median_depth = 0.f, median_weight = 0.f;
+    // 1-based list position of the median contributor, 0 = none.  (The reference keeps a float
+    // initialised to -1 and converts it to u32 at the end -- 0 after saturation; for tiles with an
+    // empty list its compiled code leaves the value uninitialised.)
+    uint32_t median_contributor = 0;
 
     int todo = n;
     for (int b = 0; b < rounds; ++b, todo -= 256) {
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             if (T > 0.5f) {
                 median_depth = depth;
                 median_weight = fmul_(T, alpha);
-                median_contributor = (float)contributor;
+                median_contributor = contributor;
             }
             N0 = fma_(T, fmul_(q3.x, alpha), N0);
             N1 = fma_(T, fmul_(q3.y, alpha), N1);
@@ -122,8 +126,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
         a.accum[pix + npix] = dist1;
         a.accum[pix + 2 * npix] = dist2;
         a.n_contrib[pix] = last_contributor;
-        // float -> u32 conversion saturates -1 to 0, as the reference's implicit cast does
-        a.n_contrib[pix + npix] = (uint32_t)__float2uint_rz(median_contributor);
+        a.n_contrib[pix + npix] = median_contributor;
         a.out_color[pix] = fma_(__ldg(a.bg + 0), T, C0);
         a.out_color[pix + npix] = fma_(__ldg(a.bg + 1), T, C1);
         a.out_color[pix + 2 * npix] = fma_(__ldg(a.bg + 2), T, C2);

@@ -41,6 +41,7 @@ struct BinArgs {
     uint2* ranges;               // [ntiles] out
     uint32_t* counters;          // [4]: num_rendered, big_count, overflow, spare
     uint32_t* big_list;          // [ntiles] scratch
+    uint32_t* tile_order;        // [ntiles] out: tiles by descending instance count (launch order of the blend CTAs)
     uint64_t* entries;           // [capacity] scratch: depth_bits<<32 | gaussian idx, bucketed by tile
     uint32_t* point_list;        // [capacity] out: per-tile depth-sorted gaussian indices
 };
@@ -49,6 +50,7 @@ struct RenderFwdArgs {
     int W, H, gx, gy;
     uint32_t capacity;
     const uint2* ranges;
+    const uint32_t* tile_order;  // [ntiles]: CTA i renders tile tile_order[i] (heaviest first)
     const uint32_t* point_list;
     const float4* rec;
     const float* bg;             // [3] device
@@ -62,6 +64,7 @@ struct RenderBwdArgs {
     int W, H, gx, gy;
     uint32_t capacity;
     const uint2* ranges;
+    const uint32_t* tile_order;
     const uint32_t* point_list;
     const float4* rec;
     const float* bg;
