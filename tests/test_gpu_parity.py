@@ -1,6 +1,6 @@
 """GPU parity of the CUDA path, through the C ABI:
   * against the UNMODIFIED reference build (oracle/_ref) on the same device: tile/sort indices,
-    radii, n_contrib and all aux maps bit-exact; colour within 1e-6; gradients within 1e-4
+    radii, n_contrib, colour and all aux maps bit-exact; gradients within 1e-4
     (the reference's own run-to-run atomic noise is ~1e-6),
   * against the CPU oracle and the committed golden fixtures (no oracle/_ref needed)."""
 import numpy as np
@@ -68,8 +68,8 @@ def test_forward_state_bit_exact_vs_reference(reference, cuda_device, P, H, W, s
     assert np.array_equal(mine["n_contrib"][1][mask], r["n_contrib"][1][mask])
     assert np.array_equal(mine["accum"].view(np.int32), r["accum"].view(np.int32))
     assert np.array_equal(mine["allmap"].view(np.int32), r["allmap"].view(np.int32))   # all 8 aux maps bit-exact
-    assert rel_err(mine["rgb"][vis], r["rgb"][vis]) < 1e-6
-    assert rel_err(mine["color"], r["color"]) < 1e-6
+    assert np.array_equal(mine["rgb"][vis].view(np.int32), r["rgb"][vis].view(np.int32))     # SH evaluation is op-pinned too
+    assert np.array_equal(mine["color"].view(np.int32), r["color"].view(np.int32))
 
 
 @pytest.mark.parametrize("P,H,W,seed,deg,bgv", CASES[:4])
@@ -130,7 +130,7 @@ def test_candidate_vs_golden_fixtures(cuda_device, path):
     assert np.array_equal(mine["ranges"], z["ranges"])
     assert np.array_equal(mine["n_contrib"][0], z["n_contrib"][0])
     assert np.array_equal(mine["allmap"].view(np.int32), z["allmap"].view(np.int32))
-    assert rel_err(mine["color"], z["color"]) < 1e-6
+    assert np.array_equal(mine["color"].view(np.int32), z["color"].view(np.int32))
     for a, b in (("g_means3D", "g_means3D"), ("g_sh", "g_shs"), ("g_opacities", "g_opacities"), ("g_scales", "g_scales"),
                  ("g_rotations", "g_rotations"), ("g_means2D", "g_means2D")):
         assert rel_err(mine[a], z[b]) < 1e-4, a
