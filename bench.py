@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--P", type=int, default=131072)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a step are spread over")
+    ap.add_argument("--skip-value", action="store_true", help="diagnostic: skip the resident-input timing loop")
     return ap.parse_args()
 
 
@@ -271,17 +273,20 @@ def main():
 
     def step():
         grads.zero_()
-        sharded.render_views(params, my_sets, upstream, grads=grads, view_ids=my_ids)
+        sharded.render_views(params, my_sets, upstream, grads=grads, view_ids=my_ids, streams=args.streams)
         grads.all_reduce()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
+    for _ in range(0 if args.skip_value else args.warmup):
         flush.zero_(); step()
     torch.cuda.synchronize(dev)
     if sampler:
         sampler.start()
-    ms, wall = timed_steps(step, args.steps, 0, flush, world, dev)
+    if args.skip_value:
+        ms, wall = 1.0, 0.0
+    else:
+        ms, wall = timed_steps(step, args.steps, 0, flush, world, dev)
     value = total_views * args.steps / (ms / 1e3)
 
     # ---- end to end through the reference-facing API, host buffers in / gradients out
@@ -367,7 +372,7 @@ def main():
             "config": {"workload": f"scene({args.P},seed0) {args.size}x{args.size} sh1 white bg, {V} views/GPU/step fwd+bwd, "
                                    f"view-sharded over {world} GPU(s) + 1 NCCL all-reduce of param grads",
                        "views_per_gpu": V, "global_views_per_step": total_views,
-                       "parallelism": f"view-shard x{world}",
+                       "parallelism": f"view-shard x{world}", "streams_per_gpu": args.streams,
                        "l2": "flushed between steps (256 MiB write, untimed)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "diff_surfel_rasterization.GaussianRasterizer + autograd, pinned host in / grads out"},

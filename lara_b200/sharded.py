@@ -59,28 +59,67 @@ class GradBuffer:
 def render_views(params: Dict[str, torch.Tensor], settings_list: Sequence[R.GaussianRasterizationSettings],
                  upstream: Callable[[int, torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                  grads: Optional[GradBuffer] = None, view_ids: Optional[Sequence[int]] = None,
-                 raster_fn=None):
+                 raster_fn=None, streams: int = 1, _pool: Optional[dict] = None):
     """Forward+backward of the given views, accumulating parameter gradients into `grads`.
 
     params   : dict with contiguous fp32 CUDA tensors means3D [P,3], shs [P,M,3], opacities [P,1],
                scales [P,2], rotations [P,4] (already activated, as LaRa's renderer passes them)
     upstream : callback (view_id, color[3,H,W], allmap[8,H,W]) -> (dL_dcolor, dL_dallmap); this is
-               where the caller's loss lives
-    raster_fn: test hook -- a callable replacing (forward_raw, backward_raw); default: the CUDA path
+               where the caller's loss lives (it runs on the stream the view was rendered on)
+    streams  : >1 renders the views round-robin on that many CUDA streams.  Views are independent,
+               so the latency-bound per-view kernels (preprocess, tile scan, scatter, per-tile
+               sort) and the tail of one view's blend overlap with another view's blend.  Each
+               stream accumulates into its own GradBuffer; they are summed into `grads` at the end.
+    raster_fn: test hook -- a callable pair replacing (forward_raw, backward_raw)
     Returns (list of (color, allmap, radii) per view, grads).
     """
     P = int(params["means3D"].shape[0])
     M = int(params["shs"].shape[1])
+    dev = params["means3D"].device
     if grads is None:
-        grads = GradBuffer(P, M, params["means3D"].device)
+        grads = GradBuffer(P, M, dev)
     fwd, bwd = raster_fn if raster_fn is not None else (R.forward_raw, R.backward_raw)
     outs = []
     ids = list(view_ids) if view_ids is not None else list(range(len(settings_list)))
-    for vid, rs in zip(ids, settings_list):
+
+    def one_view(vid, rs, gbuf):
         color, allmap, radii, state = fwd(params["means3D"], params["shs"], None, params["opacities"],
                                           params["scales"], params["rotations"], None, rs)
         g_color, g_allmap = upstream(vid, color, allmap)
         bwd(state, radii, params["means3D"], params["shs"], None, params["scales"], params["rotations"], None,
-            rs, g_color, g_allmap, out=grads.views, accumulate=True, need_means2D=False)
-        outs.append((color, allmap, radii))
+            rs, g_color, g_allmap, out=gbuf.views, accumulate=True, need_means2D=False)
+        return color, allmap, radii
+
+    n_streams = max(1, min(int(streams), len(ids)))
+    if n_streams == 1 or not params["means3D"].is_cuda:
+        for vid, rs in zip(ids, settings_list):
+            outs.append(one_view(vid, rs, grads))
+        return outs, grads
+
+    pool = _pool if _pool is not None else _STREAM_POOL
+    key = (dev.index, n_streams, P, M)
+    if key not in pool:
+        pool[key] = ([torch.cuda.Stream(device=dev) for _ in range(n_streams)],
+                     [GradBuffer(P, M, dev) for _ in range(n_streams - 1)])
+    side_streams, side_bufs = pool[key]
+    main = torch.cuda.current_stream(dev)
+    bufs = [grads] + list(side_bufs)
+    for b in side_bufs:
+        b.zero_()
+    for s in side_streams:
+        s.wait_stream(main)
+    for k, (vid, rs) in enumerate(zip(ids, settings_list)):
+        s = side_streams[k % n_streams]
+        with torch.cuda.stream(s):
+            o = one_view(vid, rs, bufs[k % n_streams])
+        for t in o:
+            t.record_stream(main)
+        outs.append(o)
+    for s in side_streams:
+        main.wait_stream(s)
+    for b in side_bufs:
+        grads.flat.add_(b.flat)
     return outs, grads
+
+
+_STREAM_POOL: dict = {}

@@ -67,6 +67,13 @@ def test_view_sharded_accumulation_equals_sum_of_views(cuda_device, big):
             acc[k] += g["g_" + k]
     for k in acc:
         assert rel_err(grads.views[k].cpu().numpy(), acc[k]) < 1e-5, k
+    # the multi-stream schedule must give the same images (bit-exact) and the same gradient sum
+    outs2, grads2 = sharded.render_views(params, sets, lambda vid, c, a: ups[vid], streams=2)
+    torch.cuda.synchronize()
+    for (c1, a1, r1), (c2, a2, r2) in zip(outs, outs2):
+        assert torch.equal(c1, c2) and torch.equal(a1, a2) and torch.equal(r1, r2)
+    for k in acc:
+        assert rel_err(grads2.views[k].cpu().numpy(), acc[k]) < 1e-5, k
 
 
 def test_lara_sized_scene_runs(cuda_device):
