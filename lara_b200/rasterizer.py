@@ -93,6 +93,42 @@ def _slot(device: torch.device) -> torch.Tensor:
     return s
 
 
+_events: dict = {}
+
+
+def _event(device: torch.device) -> "torch.cuda.Event":
+    """One reusable CUDA event per device (the forward waits on it before returning)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    e = _events.get(idx)
+    if e is None:
+        e = torch.cuda.Event()
+        _events[idx] = e
+    return e
+
+
+def _raw_stream(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class _DeviceGuard:
+    """`with torch.cuda.device(d)` only when d is not already current (the common case)."""
+
+    def __init__(self, device: torch.device):
+        self.idx = device.index
+        self.ctx = None
+
+    def __enter__(self):
+        if self.idx is not None and self.idx != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(self.idx)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def initial_capacity(P: int, device: torch.device) -> int:
     """Optimistic instance capacity for the binning buffers of a forward call."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -130,14 +166,14 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tran
     M = int(shs.shape[1]) if shs is not None else 0
     geom_b, tile_b, image_b, _ = _sizes(lib, P, H, W)
 
-    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
-    allmap = torch.empty((8, H, W), dtype=torch.float32, device=device)
+    # few, large allocations: the colour and aux maps share one [11,H,W] buffer, the three state
+    # workspaces one byte blob (sub-blobs stay 256-byte aligned: the sizes are multiples of 256)
+    out = torch.empty((11, H, W), dtype=torch.float32, device=device)
+    color, allmap = out[:3], out[3:]
     radii = torch.empty((P,), dtype=torch.int32, device=device)
-    geom = _blob(geom_b, device)
-    tile = _blob(tile_b, device)
-    image = _blob(image_b, device)
-    stream = torch.cuda.current_stream(device)
-    sptr = stream.cuda_stream
+    blob = _blob(geom_b + tile_b + image_b, device)
+    geom, tile, image = blob[:geom_b], blob[geom_b:geom_b + tile_b], blob[geom_b + tile_b:]
+    sptr = _raw_stream(device)
 
     if P == 0:
         # reference: zero-filled outputs, nothing rendered (rasterize_points.cu:92-94,105)
@@ -160,8 +196,8 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tran
         float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
         1 if raster_settings.prefiltered else 0,
         radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot.data_ptr()), lib)
-    ev = torch.cuda.Event()
-    ev.record(stream)
+    ev = _event(device)
+    ev.record()
 
     # Optimistic capacity: stage 2 is enqueued before num_rendered is known on the host, so
     # the GPU never idles behind the read-back; an overflow (rare) just re-runs stage 2.
@@ -201,29 +237,27 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
     M = int(shs.shape[1]) if shs is not None else 0
     out = out or {}
 
-    def get(name, shape):
-        t = out.get(name)
-        if t is None:
-            if accumulate:
-                return torch.zeros(shape, dtype=torch.float32, device=device)
-            return torch.empty(shape, dtype=torch.float32, device=device)
-        return t
-
-    g = {
-        "means3D": get("means3D", (P, 3)),
-        "means2D": get("means2D", (P, 3)) if need_means2D else None,
-        "sh": get("sh", (P, M, 3)) if shs is not None else None,
-        "colors_precomp": get("colors_precomp", (P, 3)) if colors_precomp is not None else None,
-        "opacities": get("opacities", (P, 1)),
-        "scales": get("scales", (P, 2)),
-        "rotations": get("rotations", (P, 4)),
-        "cov3Ds_precomp": get("cov3Ds_precomp", (P, 9)) if transMat_precomp is not None else None,
-    }
+    shapes = {"means3D": (P, 3), "means2D": (P, 3) if need_means2D else None,
+              "sh": (P, M, 3) if shs is not None else None,
+              "colors_precomp": (P, 3) if colors_precomp is not None else None,
+              "opacities": (P, 1), "scales": (P, 2), "rotations": (P, 4),
+              "cov3Ds_precomp": (P, 9) if transMat_precomp is not None else None}
+    g = {k: out.get(k) for k in shapes}
+    missing = [k for k, shp in shapes.items() if shp is not None and g[k] is None]
+    if missing:
+        # one allocation for all gradients that the caller did not supply (16-byte aligned segments)
+        sizes = [(-(-int(torch.Size(shapes[k]).numel()) // 4)) * 4 for k in missing]
+        flat = (torch.zeros if accumulate else torch.empty)(sum(sizes), dtype=torch.float32, device=device)
+        o = 0
+        for k, sz in zip(missing, sizes):
+            n = int(torch.Size(shapes[k]).numel())
+            g[k] = flat[o:o + n].view(shapes[k])
+            o += sz
     if P == 0:
         return g
     _, _, _, scratch_b = _sizes(lib, P, H, W)
     scratch = _blob(scratch_b, device)
-    sptr = torch.cuda.current_stream(device).cuda_stream
+    sptr = _raw_stream(device)
     _lib.check(lib.srf_backward(
         sptr, P, int(raster_settings.sh_degree), M, H, W,
         state.capacity, _ptr(raster_settings.bg),
@@ -307,7 +341,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         _check_settings(raster_settings, means3D.device)
         (means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c) = _normalise_inputs(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
-        with torch.cuda.device(means3D_c.device):
+        with _DeviceGuard(means3D_c.device):
             color, allmap, radii, state = forward_raw(
                 means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
         ctx.raster_settings = raster_settings
@@ -333,7 +367,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         state = ForwardState(geom, tile, image, point_list, ctx.capacity, ctx.num_rendered)
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
         grad_depth = _f32c(grad_depth, "dL_dout_others")
-        with torch.cuda.device(means3D.device):
+        with _DeviceGuard(means3D.device):
             g = backward_raw(state, radii, means3D,
                              sh if has_sh else None, colors_c if has_col else None,
                              scales if has_sc else None, rotations if has_rot else None,
