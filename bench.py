@@ -328,8 +328,15 @@ def main():
     if rank == 0:
         _lib.profile_begin()
     prof_steps = min(args.steps, 5)
+
+    def step_single_stream():
+        # per-kernel durations are only meaningful without concurrent kernels from other streams
+        grads.zero_()
+        sharded.render_views(params, my_sets, upstream, grads=grads, view_ids=my_ids, streams=1)
+        grads.all_reduce()
+
     for _ in range(prof_steps):
-        flush.zero_(); step()
+        flush.zero_(); step_single_stream()
     torch.cuda.synchronize(dev)
     if rank == 0:
         kern = _lib.profile_end()
