@@ -291,21 +291,28 @@ def main():
 
     # ---- end to end through the reference-facing API, host buffers in / gradients out
     pinned = {k: sc[k].pin_memory() for k in ("means3D", "shs", "opacities", "scales", "rotations")}
-    cam_host = [(cams[i].viewmatrix.pin_memory(), cams[i].projmatrix.pin_memory(), cams[i].campos.pin_memory()) for i in my_ids]
+    # all cameras of the step travel in one pinned buffer: [V, 16 view | 16 proj | 3 campos | pad]
+    cam_host = torch.zeros((len(my_ids), 36), dtype=torch.float32)
+    for r_, i in enumerate(my_ids):
+        cam_host[r_, 0:16] = cams[i].viewmatrix.reshape(-1)
+        cam_host[r_, 16:32] = cams[i].projmatrix.reshape(-1)
+        cam_host[r_, 32:35] = cams[i].campos
+    cam_host = cam_host.pin_memory()
     bg_dev = bg.to(dev)
     host_out = torch.empty(grads.flat.numel(), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * 4 for t in pinned.values()) + sum(sum(t.numel() * 4 for t in c) for c in cam_host)
+    h2d = sum(t.numel() * 4 for t in pinned.values()) + cam_host.numel() * 4
     d2h = host_out.numel() * 4
 
     def step_e2e():
         dp = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in pinned.items()}
         m2d = torch.zeros_like(dp["means3D"], requires_grad=True)
-        for (vm, pm, cp), i in zip(cam_host, my_ids):
+        cam_dev = cam_host.to(dev, non_blocking=True)
+        for r_, i in enumerate(my_ids):
             c = cams[i]
             rs = DSR.GaussianRasterizationSettings(
                 image_height=c.image_height, image_width=c.image_width, tanfovx=c.tanfovx, tanfovy=c.tanfovy,
-                bg=bg_dev, scale_modifier=1.0, viewmatrix=vm.to(dev, non_blocking=True),
-                projmatrix=pm.to(dev, non_blocking=True), sh_degree=1, campos=cp.to(dev, non_blocking=True),
+                bg=bg_dev, scale_modifier=1.0, viewmatrix=cam_dev[r_, 0:16].view(4, 4),
+                projmatrix=cam_dev[r_, 16:32].view(4, 4), sh_degree=1, campos=cam_dev[r_, 32:35],
                 prefiltered=False, debug=False)
             rast = DSR.GaussianRasterizer(raster_settings=rs)
             color, radii, allmap = rast(means3D=dp["means3D"], means2D=m2d, shs=dp["shs"], opacities=dp["opacities"],

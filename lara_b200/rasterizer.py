@@ -275,6 +275,20 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
     return g
 
 
+def _dump_snapshot(path: str, items) -> None:
+    """CPU copies of the call's tensors, like the reference's cpu_deep_copy_tuple + torch.save."""
+    try:
+        def cpu(x):
+            if isinstance(x, torch.Tensor):
+                return x.detach().cpu().clone()
+            if isinstance(x, tuple) and hasattr(x, "_fields"):
+                return tuple(cpu(v) for v in x)
+            return x
+        torch.save(tuple(cpu(i) for i in items), path)
+    except Exception:
+        pass
+
+
 def _check_settings(rs: GaussianRasterizationSettings, device) -> None:
     for name in ("bg", "viewmatrix", "projmatrix", "campos"):
         t = getattr(rs, name)
@@ -341,9 +355,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         _check_settings(raster_settings, means3D.device)
         (means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c) = _normalise_inputs(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
-        with _DeviceGuard(means3D_c.device):
-            color, allmap, radii, state = forward_raw(
-                means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
+        try:
+            with _DeviceGuard(means3D_c.device):
+                color, allmap, radii, state = forward_raw(
+                    means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
+        except Exception:
+            if raster_settings.debug:
+                # same debugging aid as the reference (DSR __init__.py:83-90)
+                _dump_snapshot("snapshot_fw.dump", (raster_settings, means3D, sh, colors_precomp, opacities,
+                                                   scales, rotations, cov3Ds_precomp))
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            raise
         ctx.raster_settings = raster_settings
         ctx.num_rendered = state.num_rendered
         ctx.capacity = state.capacity
@@ -367,11 +389,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         state = ForwardState(geom, tile, image, point_list, ctx.capacity, ctx.num_rendered)
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
         grad_depth = _f32c(grad_depth, "dL_dout_others")
-        with _DeviceGuard(means3D.device):
-            g = backward_raw(state, radii, means3D,
-                             sh if has_sh else None, colors_c if has_col else None,
-                             scales if has_sc else None, rotations if has_rot else None,
-                             cov_c if has_cov else None, rs, grad_out_color, grad_depth)
+        try:
+            with _DeviceGuard(means3D.device):
+                g = backward_raw(state, radii, means3D,
+                                 sh if has_sh else None, colors_c if has_col else None,
+                                 scales if has_sc else None, rotations if has_rot else None,
+                                 cov_c if has_cov else None, rs, grad_out_color, grad_depth)
+        except Exception:
+            if rs.debug:
+                _dump_snapshot("snapshot_bw.dump", (rs, means3D, radii, sh, scales, rotations, grad_out_color, grad_depth))
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            raise
         # order of DSR __init__.py:144-154
         if g["opacities"].shape != ctx.opac_shape:
             g["opacities"] = g["opacities"].view(ctx.opac_shape)

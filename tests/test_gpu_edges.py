@@ -47,9 +47,10 @@ def test_everything_behind_camera(cuda_device):
         assert float(np.abs(out[k]).max()) == 0.0, k
 
 
-@pytest.mark.parametrize("n_big,expect_min", [(3000, 2049), (20000, 16385)])
+@pytest.mark.parametrize("n_big,expect_min", [(3000, 2049), (20000, 16385), (70000, 65537)])
 def test_huge_splats_cover_every_tile(cuda_device, reference, n_big, expect_min):
-    """> 2048 instances per tile -> 1024-thread shared-memory sort; > 16384 -> global-memory sort."""
+    """> 2048 instances per tile -> 1024-thread shared-memory bucket sort; > 8192 -> in-place global
+    bitonic sort; > 65536 instances in one tile is the SURVEY's stress case."""
     from lara_b200 import scene as S
     from oracle import ref as REF
     H = W = 64
