@@ -11,6 +11,8 @@
 // Instead of emitting tiles_touched for a prefix sum + duplicate pass, the kernel
 // directly counts instances per tile (tile_count[]), the first half of the
 // tile-bucketed binning that replaces the reference's global 64-bit radix sort.
+#include <cuda_fp16.h>
+
 #include "surfel_common.cuh"
 #include "surfel_kernels.h"
 
@@ -251,41 +253,59 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 rgb[2] = __ldg(a.colors_precomp + (size_t)idx * 3 + 2);
             }
             const float opac = __ldg(a.opacities + idx);
-            // Conservative screen-space box of the pixels where this splat's alpha can reach
+            // Conservative screen-space *octagon* of the pixels where this splat's alpha can reach
             // 1/255 (the blend's skip threshold): alpha >= 1/255  =>  min(rho3d, rho2d) <= tau with
             // tau = 2 ln(255 opacity).  rho2d <= tau is a disc around the AABB centre; rho3d <= tau
-            // is the projected ellipse u^2+v^2 <= tau whose exact bounds follow from the same
-            // quadratic form as the reference's AABB with diag(1,1,-1) replaced by diag(tau,tau,-1).
-            // Used only to skip work per warp; widened by a margin so it never changes a result.
-            float bx0, by0, bx1, by1;
+            // is the projected ellipse u^2+v^2 <= tau, whose exact extent along any screen direction
+            // follows from the reference's own AABB quadratic form with diag(1,1,-1) replaced by
+            // diag(tau,tau,-1) -- evaluated here along x, y, x+y and x-y.  Stored as eight fp16
+            // offsets from the centre, rounded outwards; used only to skip work per warp, and
+            // widened by a margin so that it can never change a result.
+            float lo[4], hi[4];   // x, y, x+y, x-y
             if (opac < 0.00392156862745098f) {
-                bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;   // opacity*G < 1/255 for every G <= 1
+                for (int k = 0; k < 4; ++k) { lo[k] = 3.0e38f; hi[k] = -3.0e38f; }   // opacity*G < 1/255 for every G <= 1
             } else {
                 const float tau = 2.0f * logf(opac * 255.0f) * 1.0001f + 1.0e-3f;
                 const float r2 = sqrtf(0.5f * tau);
-                bx0 = cxs - r2; bx1 = cxs + r2; by0 = cys - r2; by1 = cys + r2;
                 const float qw = tau * (Twx * Twx + Twy * Twy) - Twz * Twz;
                 if (qw < 0.0f) {
                     const float iq = 1.0f / qw;
-                    const float ex_c = (tau * (Tux * Twx + Tuy * Twy) - Tuz * Twz) * iq;
-                    const float ey_c = (tau * (Tvx * Twx + Tvy * Twy) - Tvz * Twz) * iq;
-                    const float ex_h = sqrtf(fmaxf(0.0f, ex_c * ex_c - (tau * (Tux * Tux + Tuy * Tuy) - Tuz * Tuz) * iq));
-                    const float ey_h = sqrtf(fmaxf(0.0f, ey_c * ey_c - (tau * (Tvx * Tvx + Tvy * Tvy) - Tvz * Tvz) * iq));
-                    bx0 = fminf(bx0, ex_c - ex_h); bx1 = fmaxf(bx1, ex_c + ex_h);
-                    by0 = fminf(by0, ey_c - ey_h); by1 = fmaxf(by1, ey_c + ey_h);
-                    const float mx = 1.0f + 1.0e-3f * (bx1 - bx0), my = 1.0f + 1.0e-3f * (by1 - by0);
-                    bx0 -= mx; bx1 += mx; by0 -= my; by1 += my;
+                    // rows whose projective extent we need: Tu, Tv, Tu+Tv, Tu-Tv; disc radius along each
+                    const float rx[4] = {Tux, Tvx, Tux + Tvx, Tux - Tvx};
+                    const float ry[4] = {Tuy, Tvy, Tuy + Tvy, Tuy - Tvy};
+                    const float rz[4] = {Tuz, Tvz, Tuz + Tvz, Tuz - Tvz};
+                    const float dc[4] = {cxs, cys, cxs + cys, cxs - cys};
+                    const float dr[4] = {r2, r2, 1.41421357f * r2, 1.41421357f * r2};
+                    const float mg[4] = {1.0f, 1.0f, 1.41421357f, 1.41421357f};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float c = (tau * (rx[k] * Twx + ry[k] * Twy) - rz[k] * Twz) * iq;
+                        const float h = sqrtf(fmaxf(0.0f, c * c - (tau * (rx[k] * rx[k] + ry[k] * ry[k]) - rz[k] * rz[k]) * iq));
+                        float l0 = fminf(dc[k] - dr[k], c - h), h0 = fmaxf(dc[k] + dr[k], c + h);
+                        const float m = mg[k] + 1.0e-3f * (h0 - l0);
+                        lo[k] = l0 - m - dc[k];      // offsets from the centre (x, y, x+y, x-y of it)
+                        hi[k] = h0 + m - dc[k];
+                    }
                 } else {
-                    bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;   // the tau-ellipse crosses the camera plane: unbounded
+                    for (int k = 0; k < 4; ++k) { lo[k] = -3.0e38f; hi[k] = 3.0e38f; }   // tau-ellipse crosses the camera plane: unbounded
                 }
             }
+            // fp16, rounded outwards (NaNs stay NaN: every comparison against them fails = "not culled")
+            __half2 hb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hb[k] = __halves2half2(__float2half_rd(lo[k]), __float2half_ru(hi[k]));
+            float4 cullq;
+            cullq.x = __uint_as_float(*reinterpret_cast<unsigned*>(&hb[0]));
+            cullq.y = __uint_as_float(*reinterpret_cast<unsigned*>(&hb[1]));
+            cullq.z = __uint_as_float(*reinterpret_cast<unsigned*>(&hb[2]));
+            cullq.w = __uint_as_float(*reinterpret_cast<unsigned*>(&hb[3]));
             float4* r = a.rec + (size_t)idx * SRF_REC_QUADS;
             r[0] = make_float4(Tux, Tuy, Tuz, Tvx);
             r[1] = make_float4(Tvy, Tvz, Twx, Twy);
             r[2] = make_float4(Twz, cxs, cys, opac);
             r[3] = make_float4(nx, ny, nz, pvz);
             r[4] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(clampbits));
-            r[5] = make_float4(bx0, by0, bx1, by1);
+            r[5] = cullq;
             a.depths[idx] = pvz;
         } else {
             radius = 0; x0 = y0 = x1 = y1 = 0; ntiles = 0;

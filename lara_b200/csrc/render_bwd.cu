@@ -100,8 +100,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     const size_t npix = (size_t)a.W * a.H;
     const size_t pix = (size_t)pyi * a.W + pxi;
-    const float wxmin = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, wxmax = wxmin + 7.0f;
-    const float wymin = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f, wymax = wymin + 3.0f;
+    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -176,8 +175,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
             const int jt = (c << 5) + lane;
             bool hit = false;
             if (jt < cnt && n_eff - 1 - (b * 256 + jt) < wmax) {
-                const float4 cb = s_rec[5][jt];
-                hit = !(cb.x > wxmax || cb.z < wxmin || cb.y > wymax || cb.w < wymin);
+                hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
             }
             hits = __ballot_sync(0xffffffffu, hit);
           }

@@ -26,8 +26,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     // pixel-centre rectangle of this warp's 8x4 block, for the warp-level cull
     const int lane = tid & 31, wid = tid >> 5;
-    const float wxmin = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, wxmax = wxmin + 7.0f;
-    const float wymin = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f, wymax = wymin + 3.0f;
+    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;  // overflowed optimistic capacity: host re-runs
@@ -71,8 +70,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             const int jt = (c << 5) + lane;
             bool hit = false;
             if (jt < cnt) {
-                const float4 cb = s_rec[5][jt];
-                hit = !(cb.x > wxmax || cb.z < wxmin || cb.y > wymax || cb.w < wymin);
+                hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
             }
             hits = __ballot_sync(0xffffffffu, hit);
           }

@@ -10,7 +10,8 @@
 //       q2 = Tw.z cx   cy   opacity       (cx,cy = screen-space AABB centre)
 //       q3 = n.x  n.y  n.z  depth         (view-space normal, view-space z)
 //       q4 = r    g    b    clamp-bits    (SH->RGB colour, 3 clamp flags as int bits)
-//       q5 = bx0  by0  bx1  by1          (conservative box of alpha >= 1/255, for warp culling)
+//       q5 = 8 x fp16: lo/hi offsets from (cx,cy) along x, y, x+y, x-y of a conservative octagon
+//            around {alpha >= 1/255}, for warp culling
 //
 // Every float op on the integer-critical chain (depth bits -> sort key, T -> AABB ->
 // radius -> tile rect, and the per-pixel alpha/transmittance chain that decides
@@ -18,6 +19,7 @@
 // order nvcc 12.9 emitted for the reference (sm_100 SASS of forward.cu), so that
 // fused-multiply-add contraction cannot differ between the two builds.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -120,3 +122,29 @@ __device__ __forceinline__ void tile_pixel(int tid, int& lx, int& ly) {
 }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Pixel-centre bounds of a warp's 8x4 block along x, y, x+y, x-y.
+struct WarpRect {
+    float xmin, xmax, ymin, ymax, umin, umax, vmin, vmax;
+};
+__device__ __forceinline__ WarpRect make_warp_rect(int tile_x, int tile_y, int wid) {
+    WarpRect w;
+    w.xmin = (float)(tile_x * SRF_TILE + ((wid & 1) << 3)) + 0.5f; w.xmax = w.xmin + 7.0f;
+    w.ymin = (float)(tile_y * SRF_TILE + ((wid >> 1) << 2)) + 0.5f; w.ymax = w.ymin + 3.0f;
+    w.umin = w.xmin + w.ymin; w.umax = w.xmax + w.ymax;
+    w.vmin = w.xmin - w.ymax; w.vmax = w.xmax - w.ymin;
+    return w;
+}
+// true if the splat's conservative octagon (q5, centred at q2.yz) may touch the warp's block
+__device__ __forceinline__ bool octagon_hits(const float4 q2, const float4 q5, const WarpRect& w) {
+    const float cx = q2.y, cy = q2.z;
+    const unsigned ux = __float_as_uint(q5.x), uy = __float_as_uint(q5.y), uu = __float_as_uint(q5.z), uv = __float_as_uint(q5.w);
+    const float2 ex = __half22float2(*reinterpret_cast<const __half2*>(&ux));
+    const float2 ey = __half22float2(*reinterpret_cast<const __half2*>(&uy));
+    const float2 eu = __half22float2(*reinterpret_cast<const __half2*>(&uu));
+    const float2 ev = __half22float2(*reinterpret_cast<const __half2*>(&uv));
+    const float cu = cx + cy, cv = cx - cy;
+    const bool out = (cx + ex.x > w.xmax) || (cx + ex.y < w.xmin) || (cy + ey.x > w.ymax) || (cy + ey.y < w.ymin) ||
+                     (cu + eu.x > w.umax) || (cu + eu.y < w.umin) || (cv + ev.x > w.vmax) || (cv + ev.y < w.vmin);
+    return !out;
+}
