@@ -70,7 +70,9 @@ __device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, cons
     const float Tvx = q0.w, Tvy = q1.x, Tvz = q1.y;
     const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
     const float cx = q2.y, cy = q2.z, opac = q2.w;
-    e.valid = false;
+    // Straight-line code: the reference `continue`s at five places, but within a warp those
+    // early-outs almost never agree, so the rejection tests are folded into one predicate at the
+    // end (division by p.z == 0 just yields inf/NaN, which the predicate discards).
     // k = pix.x * Tw - Tu ; l = pix.y * Tw - Tv
     e.kx = fma_(pixx, Twx, -Tux);
     e.ky = fma_(pixx, Twy, -Tuy);
@@ -82,7 +84,6 @@ __device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, cons
     e.pz = fma_(e.kx, e.ly, -fmul_(e.ky, e.lx));
     e.px = fma_(e.ky, e.lz, -fmul_(e.kz, e.ly));
     e.py = fma_(e.kz, e.lx, -fmul_(e.kx, e.lz));
-    if (e.pz == 0.0f) return;
     e.sx = __fdiv_rn(e.px, e.pz);
     e.sy = __fdiv_rn(e.py, e.pz);
     e.rho3d = fma_(e.sx, e.sx, fmul_(e.sy, e.sy));
@@ -92,17 +93,15 @@ __device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, cons
     // constant 1/(0.70710678118654762)^2 rounds the product to exactly 2*|d|^2 in fp32.
     e.rho2d = fmul_(2.0f, fma_(e.dx, e.dx, fmul_(e.dy, e.dy)));
     const float rho = fminf(e.rho3d, e.rho2d);
-    float depth = Twz;
-    if (e.rho3d <= e.rho2d) depth = fadd_(Twz, fma_(Twx, e.sx, fmul_(Twy, e.sy)));
+    const float depth3d = fadd_(Twz, fma_(Twx, e.sx, fmul_(Twy, e.sy)));
+    const float depth = (e.rho3d <= e.rho2d) ? depth3d : Twz;
     e.depth = depth;
-    // reference compares (double)depth < 0.2 (double); identical to depth < 0.2f
-    if (!(depth >= SRF_NEAR_F)) return;
     const float power = fmul_(rho, -0.5f);
-    if (power > 0.0f) return;
     e.G = expf(power);
     e.alpha = fminf(0.99f, fmul_(opac, e.G));
-    if (!(e.alpha >= 0.00392156862745098f)) return;  // alpha < 1/255
-    e.valid = true;
+    // reference: skip if p.z == 0, if (double)depth < 0.2 (== depth < 0.2f), if power > 0,
+    // if alpha < 1/255
+    e.valid = (e.pz != 0.0f) && !(depth < SRF_NEAR_F) && !(power > 0.0f) && !(e.alpha < 0.00392156862745098f);
 }
 
 // mapped depth for the distortion loss, evaluated in double exactly as the reference
