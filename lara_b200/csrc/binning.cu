@@ -157,8 +157,20 @@ __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
     }
     const int kSerialMax = 8;
     if (ntiles > 0 && ntiles <= kSerialMax) {
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) emit_instance(a, y * a.gx + x, key);
+        // claim all slots first (independent returning atomics stay in flight together), then store
+        const int w = x1 - x0;
+        uint32_t slot[kSerialMax];
+#pragma unroll
+        for (int k = 0; k < kSerialMax; ++k) {
+            slot[k] = 0xffffffffu;
+            if (k < ntiles) {
+                const int ty = k / w, tx = k - ty * w;
+                slot[k] = atomicAdd(&a.tile_count[(size_t)((y0 + ty) * a.gx + x0 + tx) * SRF_TILE_CTR_STRIDE + 1], 1u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSerialMax; ++k)
+            if (k < ntiles && slot[k] < a.capacity) a.entries[slot[k]] = key;
     }
     unsigned big = __ballot_sync(0xffffffffu, ntiles > kSerialMax);
     while (big) {

@@ -31,6 +31,18 @@ template <bool ACC>
 __device__ __forceinline__ void put(float* p, float v) {
     if (ACC) *p += v; else *p = v;
 }
+template <bool ACC>
+__device__ __forceinline__ void put4(float* p, float4 v) {   // p must be 16-byte aligned
+    float4* q = reinterpret_cast<float4*>(p);
+    if (ACC) { const float4 o = *q; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *q = v;
+}
+template <bool ACC>
+__device__ __forceinline__ void put2(float* p, float2 v) {   // p must be 8-byte aligned
+    float2* q = reinterpret_cast<float2*>(p);
+    if (ACC) { const float2 o = *q; v.x += o.x; v.y += o.y; }
+    *q = v;
+}
 
 template <bool ACC>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a) {
@@ -216,6 +228,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             dmean3D[2] += (-v.x * v.z * dL_ddir.x - v.y * v.z * dL_ddir.y + (sum2 - v.z * v.z) * dL_ddir.z) * invsum32;
         }
         const int ncoef = a.M < 16 ? a.M : 16;
+        if (a.M == 4 && a.vec_ok) {
+            // LaRa's case (degree 1): one 48-byte row = three 128-bit stores
+            const float r = dRGB[0], g = dRGB[1], b = dRGB[2];
+            put4<ACC>(out + 0, make_float4(coef[0] * r, coef[0] * g, coef[0] * b, coef[1] * r));
+            put4<ACC>(out + 4, make_float4(coef[1] * g, coef[1] * b, coef[2] * r, coef[2] * g));
+            put4<ACC>(out + 8, make_float4(coef[2] * b, coef[3] * r, coef[3] * g, coef[3] * b));
+        } else
         for (int k = 0; k < a.M; ++k) {
             const float ck = (k < ncoef) ? coef[k] : 0.f;
             put<ACC>(out + 3 * k + 0, ck * dRGB[0]);
@@ -233,10 +252,15 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         put<ACC>(a.dL_dmeans2D + 3 * (size_t)idx + 2, 0.f);
     }
     put<ACC>(a.dL_dopacity + idx, dopac);
-    put<ACC>(a.dL_dscales + 2 * (size_t)idx + 0, dscale[0]);
-    put<ACC>(a.dL_dscales + 2 * (size_t)idx + 1, dscale[1]);
+    if (a.vec_ok) {
+        put2<ACC>(a.dL_dscales + 2 * (size_t)idx, make_float2(dscale[0], dscale[1]));
+        put4<ACC>(a.dL_drotations + 4 * (size_t)idx, make_float4(drot[0], drot[1], drot[2], drot[3]));
+    } else {
+        put<ACC>(a.dL_dscales + 2 * (size_t)idx + 0, dscale[0]);
+        put<ACC>(a.dL_dscales + 2 * (size_t)idx + 1, dscale[1]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) put<ACC>(a.dL_drotations + 4 * (size_t)idx + k, drot[k]);
+        for (int k = 0; k < 4; ++k) put<ACC>(a.dL_drotations + 4 * (size_t)idx + k, drot[k]);
+    }
     if (a.dL_dcolors != nullptr) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) put<ACC>(a.dL_dcolors + 3 * (size_t)idx + k, dcol[k]);
@@ -250,11 +274,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
 cudaError_t launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t stream) {
     if (a.P <= 0) return cudaSuccess;
     const int grid = (a.P + 255) / 256;
+    PreprocessBwdArgs args = a;
+    auto al = [](const void* p, uintptr_t n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; };
+    args.vec_ok = (al(a.dL_drotations, 16) && al(a.dL_dscales, 8) && (a.dL_dsh == nullptr || al(a.dL_dsh, 16))) ? 1 : 0;
     prof_start(K_PREPROCESS_BWD, stream);
     if (a.accumulate)
-        preprocess_bwd_kernel<true><<<grid, 256, 0, stream>>>(a);
+        preprocess_bwd_kernel<true><<<grid, 256, 0, stream>>>(args);
     else
-        preprocess_bwd_kernel<false><<<grid, 256, 0, stream>>>(a);
+        preprocess_bwd_kernel<false><<<grid, 256, 0, stream>>>(args);
     prof_stop(K_PREPROCESS_BWD, stream);
     return cudaGetLastError();
 }

@@ -91,6 +91,7 @@ struct PreprocessBwdArgs {
     const float4* rec;
     const float* ggrad;          // [P,20]
     int accumulate;              // += into the outputs instead of overwriting (view-sharded accumulation)
+    int vec_ok;                  // set by the launcher: output rows are 16/8-byte aligned -> vector stores
     float* dL_dmeans3D;          // [P,3]
     float* dL_dmeans2D;          // [P,3] or null
     float* dL_dsh;               // [P,M,3] or null
