@@ -289,13 +289,20 @@ def _dump_snapshot(path: str, items) -> None:
         pass
 
 
-def _check_settings(rs: GaussianRasterizationSettings, device) -> None:
+def _check_settings(rs: GaussianRasterizationSettings, device) -> GaussianRasterizationSettings:
+    """Device / dtype checks of the settings tensors, and `.contiguous()` exactly where the reference
+    calls it (rasterize_points.cu:113-131): LaRa's MiniCam passes `w2c.transpose(0, 1)`, a
+    non-contiguous view, as the view matrix (lightning/utils.py:40)."""
+    fixed = {}
     for name in ("bg", "viewmatrix", "projmatrix", "campos"):
         t = getattr(rs, name)
         if not isinstance(t, torch.Tensor) or not t.is_cuda:
             raise RuntimeError(f"{name} must be a CUDA tensor")
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            raise RuntimeError(f"raster_settings.{name} must be a contiguous float32 tensor")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"expected scalar type Float but found {t.dtype} for raster_settings.{name}")
+        if not t.is_contiguous():
+            fixed[name] = t.contiguous()
+    return rs._replace(**fixed) if fixed else rs
 
 
 def _normalise_inputs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp):
@@ -352,7 +359,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                 cov3Ds_precomp, raster_settings):
-        _check_settings(raster_settings, means3D.device)
+        raster_settings = _check_settings(raster_settings, means3D.device)
         (means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c) = _normalise_inputs(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         try:
@@ -415,9 +422,9 @@ class GaussianRasterizer(nn.Module):
     def markVisible(self, positions):
         """Boolean mask of points in front of the near plane (DSR __init__.py:177-186)."""
         with torch.no_grad():
-            rs = self.raster_settings
             lib = _lib.load()
             pos = _f32c(positions, "means3D")
+            rs = _check_settings(self.raster_settings, pos.device)
             P = int(pos.shape[0])
             present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
             if P:

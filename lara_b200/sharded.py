@@ -83,6 +83,8 @@ def render_views(params: Dict[str, torch.Tensor], settings_list: Sequence[R.Gaus
     ids = list(view_ids) if view_ids is not None else list(range(len(settings_list)))
 
     def one_view(vid, rs, gbuf):
+        if raster_fn is None:
+            rs = R._check_settings(rs, dev)      # contiguous fp32 CUDA settings tensors, as the per-view path
         color, allmap, radii, state = fwd(params["means3D"], params["shs"], None, params["opacities"],
                                           params["scales"], params["rotations"], None, rs)
         g_color, g_allmap = upstream(vid, color, allmap)

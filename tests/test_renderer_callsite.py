@@ -46,6 +46,10 @@ def _render_img_like(mod, cam, raw, bg, dev):
     """Replays renderer_2dgs.Renderer.render_img with module `mod` as the rasterizer package."""
     from lara_b200 import scene as S
     rs = S.settings_for(cam, bg, 1, dev, mod.GaussianRasterizationSettings)
+    # MiniCam hands over w2c.transpose(0, 1): a NON-contiguous view matrix (lightning/utils.py:40)
+    w2c = rs.viewmatrix.t().contiguous()
+    rs = rs._replace(viewmatrix=w2c.transpose(0, 1))
+    assert not rs.viewmatrix.is_contiguous()
     rast = mod.GaussianRasterizer(raster_settings=rs)
     opacity = torch.sigmoid(raw["opacity"])
     scales = torch.exp(raw["scales"])
