@@ -166,10 +166,11 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tran
     M = int(shs.shape[1]) if shs is not None else 0
     geom_b, tile_b, image_b, _ = _sizes(lib, P, H, W)
 
-    # few, large allocations: the colour and aux maps share one [11,H,W] buffer, the three state
-    # workspaces one byte blob (sub-blobs stay 256-byte aligned: the sizes are multiples of 256)
-    out = torch.empty((11, H, W), dtype=torch.float32, device=device)
-    color, allmap = out[:3], out[3:]
+    # the three state workspaces share one byte blob (sub-blobs stay 256-byte aligned: the sizes are
+    # multiples of 256).  The two images stay separate tensors: outputs of an autograd.Function
+    # that are views of a common base cannot be modified in place by the caller.
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    allmap = torch.empty((8, H, W), dtype=torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
     blob = _blob(geom_b + tile_b + image_b, device)
     geom, tile, image = blob[:geom_b], blob[geom_b:geom_b + tile_b], blob[geom_b + tile_b:]

@@ -185,3 +185,31 @@ def test_non_contiguous_inputs_and_debug_flag(cuda_device):
     with pytest.raises(RuntimeError, match="Float"):
         rast(means3D=scd["means3D"].double(), means2D=torch.zeros(3000, 3, device=cuda_device), shs=scd["shs"],
              opacities=scd["opacities"], scales=scd["scales"], rotations=scd["rotations"])
+
+
+def test_outputs_can_be_modified_in_place_and_settings_may_be_strided(cuda_device):
+    """Callers clamp / scale the returned images in place; MiniCam passes a transposed (strided)
+    view matrix.  Both must work and give the same result as the plain call."""
+    from lara_b200 import scene as S
+    import diff_surfel_rasterization as DSR
+    sc = S.scene(3000, 12)
+    cam = S.cameras(1, 64, 64, 0)[0]
+    scd = to_dev(sc, cuda_device)
+    st = S.settings_for(cam, torch.ones(3), 1, cuda_device, DSR.GaussianRasterizationSettings)
+    st_strided = st._replace(viewmatrix=st.viewmatrix.t().contiguous().t())
+    assert not st_strided.viewmatrix.is_contiguous()
+    outs = []
+    for s_ in (st, st_strided):
+        m3 = scd["means3D"].clone().requires_grad_(True)
+        img, radii, allmap = DSR.GaussianRasterizer(raster_settings=s_)(
+            means3D=m3, means2D=torch.zeros_like(m3), shs=scd["shs"], opacities=scd["opacities"],
+            scales=scd["scales"], rotations=scd["rotations"])
+        ref_img = img.detach().clone()
+        img = img * 1.0
+        img.clamp_(0.0, 0.5)            # in place on a function of the output
+        allmap2 = allmap.detach().clone()
+        (img.sum() + allmap.sum()).backward()
+        assert torch.isfinite(m3.grad).all()
+        outs.append((ref_img, allmap2, m3.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-8)
