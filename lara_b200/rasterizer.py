@@ -154,11 +154,17 @@ class ForwardState(NamedTuple):
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
                 raster_settings: GaussianRasterizationSettings):
-    """Enqueue one forward on the current stream.
+    """Enqueue one forward on the current stream of the tensors' device.
 
     Returns (color[3,H,W], allmap[8,H,W], radii[P], ForwardState).  Inputs must already be
     normalised (None for absent, fp32, contiguous, CUDA).
     """
+    with _DeviceGuard(means3D.device):
+        return _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
+                            raster_settings)
+
+
+def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp, raster_settings):
     lib = _lib.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P = int(means3D.shape[0])
@@ -231,6 +237,14 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
     tensors for 'means3D','sh','opacities','scales','rotations'; with ``accumulate`` the
     kernel adds into them (view-sharded accumulation).
     """
+    with _DeviceGuard(means3D.device):
+        return _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
+                             raster_settings, grad_color, grad_allmap, out=out, accumulate=accumulate,
+                             need_means2D=need_means2D)
+
+
+def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
+                  raster_settings, grad_color, grad_allmap, *, out=None, accumulate=False, need_means2D=True):
     lib = _lib.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P = int(means3D.shape[0])
@@ -364,9 +378,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         (means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c) = _normalise_inputs(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         try:
-            with _DeviceGuard(means3D_c.device):
-                color, allmap, radii, state = forward_raw(
-                    means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
+            color, allmap, radii, state = forward_raw(
+                means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
         except Exception:
             if raster_settings.debug:
                 # same debugging aid as the reference (DSR __init__.py:83-90)
@@ -398,11 +411,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
         grad_depth = _f32c(grad_depth, "dL_dout_others")
         try:
-            with _DeviceGuard(means3D.device):
-                g = backward_raw(state, radii, means3D,
-                                 sh if has_sh else None, colors_c if has_col else None,
-                                 scales if has_sc else None, rotations if has_rot else None,
-                                 cov_c if has_cov else None, rs, grad_out_color, grad_depth)
+            g = backward_raw(state, radii, means3D,
+                             sh if has_sh else None, colors_c if has_col else None,
+                             scales if has_sc else None, rotations if has_rot else None,
+                             cov_c if has_cov else None, rs, grad_out_color, grad_depth)
         except Exception:
             if rs.debug:
                 _dump_snapshot("snapshot_bw.dump", (rs, means3D, radii, sh, scales, rotations, grad_out_color, grad_depth))
