@@ -122,6 +122,25 @@ int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat);
 
+/* ---- fused render_img epilogue (next-row: lightning/renderer_2dgs.py:220-268, :74-89) ---------
+ * One pass over the rasterizer's outputs instead of ~12 torch ops (and ~20 autograd ops):
+ * image = clamp(color,0,1); acc_map = alpha; rend_normal = viewmatrix[:3,:3] . normal;
+ * depth = nan_to_num(D/alpha)*(1-depth_ratio) + depth_ratio*nan_to_num(median depth);
+ * depth_normal = alpha * normalize(cross(d/drow, d/dcol of (ray_o + depth*ray_d))) on interior pixels;
+ * rend_dist = distortion.  All images planar [C,H,W] fp32; rays [H,W,6] may be NULL (no pseudo
+ * normals).  The backward takes the gradients of the six outputs (NULL = zero) and writes
+ * dL_dcolor [3,H,W] and dL_dallmap [8,H,W], ready for srf_backward; where the reference's
+ * autograd produces NaN (0/0 at alpha == 0) this writes 0.  scratch: [3,H,W] floats.          */
+int srf_epilogue_forward(srf_stream_t stream, int image_height, int image_width, float depth_ratio,
+                         const float* color, const float* allmap, const float* rays, const float* viewmatrix,
+                         float* image, float* depth, float* acc_map, float* rend_normal, float* depth_normal,
+                         float* rend_dist);
+int srf_epilogue_backward(srf_stream_t stream, int image_height, int image_width, float depth_ratio,
+                          const float* color, const float* allmap, const float* rays, const float* viewmatrix,
+                          const float* g_image, const float* g_depth, const float* g_acc_map,
+                          const float* g_rend_normal, const float* g_depth_normal, const float* g_rend_dist,
+                          float* scratch, float* dL_dcolor, float* dL_dallmap);
+
 /* ---- optional per-kernel timing (no reference counterpart; used by bench.py's roofline) --
  * Between srf_profile_begin() and srf_profile_end() every kernel launch made by this
  * library is bracketed by CUDA events on its launching stream.  srf_profile_end waits for

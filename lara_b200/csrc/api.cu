@@ -372,6 +372,44 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
     return 0;
 }
 
+int srf_epilogue_forward(srf_stream_t stream_, int image_height, int image_width, float depth_ratio,
+                         const float* color, const float* allmap, const float* rays, const float* viewmatrix,
+                         float* image, float* depth, float* acc_map, float* rend_normal, float* depth_normal,
+                         float* rend_dist) {
+    if (image_height <= 0 || image_width <= 0) return fail("srf_epilogue_forward: bad sizes");
+    if (!color || !allmap || !viewmatrix || !image || !depth || !acc_map || !rend_normal || !depth_normal || !rend_dist)
+        return fail("srf_epilogue_forward: null pointer");
+    srf::EpilogueArgs a;
+    memset(&a, 0, sizeof(a));
+    a.W = image_width; a.H = image_height; a.depth_ratio = depth_ratio;
+    a.color = color; a.allmap = allmap; a.rays = rays; a.viewmatrix = viewmatrix;
+    a.image = image; a.depth = depth; a.acc = acc_map; a.rend_normal = rend_normal; a.depth_normal = depth_normal;
+    a.dist = rend_dist;
+    cudaError_t e = srf::launch_epilogue_fwd(a, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("epilogue_fwd launch", e);
+    return 0;
+}
+
+int srf_epilogue_backward(srf_stream_t stream_, int image_height, int image_width, float depth_ratio,
+                          const float* color, const float* allmap, const float* rays, const float* viewmatrix,
+                          const float* g_image, const float* g_depth, const float* g_acc_map,
+                          const float* g_rend_normal, const float* g_depth_normal, const float* g_rend_dist,
+                          float* scratch, float* dL_dcolor, float* dL_dallmap) {
+    if (image_height <= 0 || image_width <= 0) return fail("srf_epilogue_backward: bad sizes");
+    if (!color || !allmap || !viewmatrix || !dL_dcolor || !dL_dallmap) return fail("srf_epilogue_backward: null pointer");
+    if (g_depth_normal && rays && !scratch) return fail("srf_epilogue_backward: scratch [3,H,W] required");
+    srf::EpilogueArgs a;
+    memset(&a, 0, sizeof(a));
+    a.W = image_width; a.H = image_height; a.depth_ratio = depth_ratio;
+    a.color = color; a.allmap = allmap; a.rays = rays; a.viewmatrix = viewmatrix;
+    a.g_image = g_image; a.g_depth = g_depth; a.g_acc = g_acc_map; a.g_rend_normal = g_rend_normal;
+    a.g_depth_normal = g_depth_normal; a.g_dist = g_rend_dist;
+    a.scratch = scratch; a.dL_dcolor = dL_dcolor; a.dL_dallmap = dL_dallmap;
+    cudaError_t e = srf::launch_epilogue_bwd(a, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("epilogue_bwd launch", e);
+    return 0;
+}
+
 int srf_mark_visible(srf_stream_t stream_, int P, const float* means3D,
                      const float* viewmatrix, const float* projmatrix, uint8_t* present) {
     (void)projmatrix;

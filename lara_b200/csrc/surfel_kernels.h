@@ -102,6 +102,31 @@ struct PreprocessBwdArgs {
     float* dL_dtransMat;         // [P,9] or null
 };
 
+// Fused render_img epilogue; all images planar [C,H,W] fp32.
+struct EpilogueArgs {
+    int W, H;
+    float depth_ratio;
+    const float* color;          // [3,H,W] rasterizer colour
+    const float* allmap;         // [8,H,W] rasterizer aux maps
+    const float* rays;           // [H,W,6] or null (then no pseudo normals)
+    const float* viewmatrix;     // [16]
+    // forward outputs
+    float* image;                // [3,H,W]
+    float* depth;                // [1,H,W]
+    float* acc;                  // [H,W]
+    float* rend_normal;          // [3,H,W]
+    float* depth_normal;         // [3,H,W]
+    float* dist;                 // [H,W]
+    // backward inputs (any may be null = zero) and outputs
+    const float* g_image; const float* g_depth; const float* g_acc;
+    const float* g_rend_normal; const float* g_depth_normal; const float* g_dist;
+    float* scratch;              // [3,H,W]
+    float* dL_dcolor;            // [3,H,W]
+    float* dL_dallmap;           // [8,H,W]
+};
+cudaError_t launch_epilogue_fwd(const EpilogueArgs& a, cudaStream_t stream);
+cudaError_t launch_epilogue_bwd(const EpilogueArgs& a, cudaStream_t stream);
+
 // Optional per-kernel CUDA-event timing (srf_profile_begin/end in the C ABI); no-ops unless enabled.
 enum KernelId { K_PREPROCESS_FWD = 0, K_TILE_SCAN, K_SCATTER, K_SORT_SMALL, K_SORT_BIG, K_RENDER_FWD,
                 K_RENDER_BWD, K_PREPROCESS_BWD, K_COUNT };

@@ -1,0 +1,112 @@
+"""Fused epilogue of LaRa's ``Renderer.render_img`` -- an additional entry
+point next to the unchanged drop-in rasterizer.
+
+``render_img_epilogue(color, allmap, rays, viewmatrix, depth_ratio, prex)`` returns exactly the
+dict ``lightning/renderer_2dgs.py:256-268`` returns (same keys, shapes and -- permuted-view --
+memory layout), computed by one CUDA kernel instead of ~12 torch ops, with a fused backward that
+feeds ``dL_dcolor`` / ``dL_dallmap`` straight into the rasterizer's backward.  A maintainer can
+switch ``Renderer.render_img`` to it with a two-line change::
+
+    rendered_image, radii, allmap = rasterizer(...)            # unchanged
+    if rays is None: return rendered_image.clamp(0, 1)
+    return render_img_epilogue(rendered_image, allmap, rays, cam.world_view_transform, depth_ratio, prex)
+
+One deliberate difference: where the reference's autograd produces NaN gradients (0/0 in the
+backward of ``D / alpha`` at pixels with alpha == 0) the fused backward produces 0.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .rasterizer import _DeviceGuard, _raw_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.contiguous()
+
+
+class _Epilogue(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, color, allmap, rays, viewmatrix, depth_ratio):
+        lib = _lib.load()
+        color = color.contiguous(); allmap = allmap.contiguous()
+        viewmatrix = viewmatrix.contiguous()
+        rays_c = rays.contiguous() if rays is not None else None
+        if color.dtype != torch.float32 or allmap.dtype != torch.float32 or not color.is_cuda:
+            raise RuntimeError("render_img_epilogue expects fp32 CUDA tensors")
+        H, W = int(color.shape[1]), int(color.shape[2])
+        dev = color.device
+        def new(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+        # separate planar tensors; the [H,W,C] permutes happen outside the Function so that the
+        # results are ordinary autograd views (callers may then modify them in place)
+        image, depth, acc, rn, dn, dist = new(3, H, W), new(1, H, W), new(H, W), new(3, H, W), new(3, H, W), new(H, W)
+        with _DeviceGuard(dev):
+            _lib.check(lib.srf_epilogue_forward(
+                _raw_stream(dev), H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays_c),
+                viewmatrix.data_ptr(), image.data_ptr(), depth.data_ptr(), acc.data_ptr(), rn.data_ptr(),
+                dn.data_ptr(), dist.data_ptr()), lib)
+        ctx.save_for_backward(color, allmap, rays_c if rays_c is not None else color.new_empty(0), viewmatrix)
+        ctx.has_rays = rays_c is not None
+        ctx.depth_ratio = float(depth_ratio)
+        return image, depth, acc, rn, dn, dist
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_acc, g_rn, g_dn, g_dist):
+        lib = _lib.load()
+        color, allmap, rays, viewmatrix = ctx.saved_tensors
+        rays = rays if ctx.has_rays else None
+        H, W = int(color.shape[1]), int(color.shape[2])
+        dev = color.device
+        gi, gd, ga, grn, gdn, gds = _c(g_image), _c(g_depth), _c(g_acc), _c(g_rn), _c(g_dn), _c(g_dist)
+        buf = torch.empty((14, H, W), dtype=torch.float32, device=dev)
+        scratch, d_color, d_allmap = buf[0:3], buf[3:6], buf[6:14]
+        with _DeviceGuard(dev):
+            _lib.check(lib.srf_epilogue_backward(
+                _raw_stream(dev), H, W, ctx.depth_ratio, color.data_ptr(), allmap.data_ptr(), _p(rays),
+                viewmatrix.data_ptr(), _p(gi), _p(gd), _p(ga), _p(grn), _p(gdn), _p(gds),
+                scratch.data_ptr(), d_color.data_ptr(), d_allmap.data_ptr()), lib)
+        return d_color, d_allmap, None, None, None
+
+
+def render_img_epilogue(rendered_image: torch.Tensor, allmap: torch.Tensor, rays: Optional[torch.Tensor],
+                        world_view_transform: torch.Tensor, depth_ratio: float = 0.0, prex: str = "") -> Dict[str, torch.Tensor]:
+    """The dict of ``Renderer.render_img`` (renderer_2dgs.py:256-268) from the rasterizer's outputs."""
+    image, depth, acc, rn, dn, dist = _Epilogue.apply(rendered_image, allmap, rays, world_view_transform, depth_ratio)
+    return {
+        f"image{prex}": image.permute(1, 2, 0), f"depth{prex}": depth.permute(1, 2, 0), f"acc_map{prex}": acc,
+        f"rend_normal{prex}": rn.permute(1, 2, 0), f"depth_normal{prex}": dn.permute(1, 2, 0), f"rend_dist{prex}": dist,
+    }
+
+
+def render_img_epilogue_torch(rendered_image, allmap, rays, world_view_transform, depth_ratio=0.0, prex=""):
+    """Plain-torch restatement of renderer_2dgs.py:220-268 (+ depth_to_normal :74-89).
+
+    Test/measurement reference for the fused kernel -- this is what LaRa executes today."""
+    rendered_image = rendered_image.clamp(0, 1)
+    render_alpha = allmap[1:2]
+    render_normal = allmap[2:5]
+    render_normal = (render_normal.permute(1, 2, 0) @ (world_view_transform[:3, :3].T)).permute(2, 0, 1)
+    render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
+    render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+    render_dist = allmap[6:7]
+    surf_depth = render_depth_expected * (1 - depth_ratio) + depth_ratio * render_depth_median
+    points = (rays[..., :3].reshape(-1, 3) + surf_depth.reshape(-1, 1) * rays[..., 3:].reshape(-1, 3)).reshape(
+        *surf_depth.shape[1:], 3)
+    output = torch.zeros_like(points)
+    dx = points[2:, 1:-1] - points[:-2, 1:-1]
+    dy = points[1:-1, 2:] - points[1:-1, :-2]
+    output[1:-1, 1:-1, :] = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    surf_normal = output.permute(2, 0, 1) * render_alpha.detach()
+    return {
+        f"image{prex}": rendered_image.permute(1, 2, 0), f"depth{prex}": surf_depth.permute(1, 2, 0),
+        f"acc_map{prex}": render_alpha.squeeze(0), f"rend_normal{prex}": render_normal.permute(1, 2, 0),
+        f"depth_normal{prex}": surf_normal.permute(1, 2, 0), f"rend_dist{prex}": render_dist.squeeze(0),
+    }
