@@ -121,3 +121,55 @@ def test_fused_epilogue_feeds_rasterizer_backward(cuda_device):
         grads.append({k: torch.nan_to_num(v.grad).cpu().numpy() for k, v in leaves.items()})
     for k in grads[0]:
         assert rel_err(grads[0][k], grads[1][k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_fast_renderer_matches_reference_pipeline(cuda_device, reference):
+    """lara_b200.renderer.Renderer.render_img == reference rasterizer + the torch epilogue (the
+    pipeline LaRa runs today), images and raw-parameter gradients."""
+    import types
+    from lara_b200 import scene as S
+    from lara_b200.epilogue import render_img_epilogue_torch
+    from lara_b200.renderer import Renderer
+    dev = cuda_device
+    H = W = 160
+    sc = S.scene(30000, 21)
+    c = S.cameras(2, H, W, 5)[1]
+    cam = types.SimpleNamespace(image_height=H, image_width=W, FoVx=0.75, FoVy=0.75,
+                                world_view_transform=c.viewmatrix.to(dev), full_proj_transform=c.projmatrix.to(dev),
+                                camera_center=c.campos.to(dev))
+    _, _, rays, _ = _inputs(H, W, 3, dev)
+    base = {"centers": sc["means3D"], "shs": sc["shs"], "opacity": torch.logit(sc["opacities"].clamp(1e-4, 1 - 1e-4)),
+            "scales": torch.log(sc["scales"]), "rotations": sc["rotations"] * 0.7}
+
+    def loss_of(out):
+        mask = (out["acc_map"] > 0).detach()
+        return ((out["image"] - 0.4) ** 2).mean() + 0.2 * (out["rend_normal"] ** 2).mean() + 1000.0 * out["rend_dist"].mean() \
+            + 0.1 * (out["depth"][..., 0] * mask).mean() + out["acc_map"].mean() \
+            + 0.2 * (1 - (out["rend_normal"] * out["depth_normal"]).sum(-1)).mean()
+
+    res = []
+    # (a) this repo's fast Renderer
+    raw = {k: v.to(dev).clone().requires_grad_(True) for k, v in base.items()}
+    r = Renderer(sh_degree=1, white_background=True)
+    out = r.render_img(cam, rays, raw["centers"], raw["shs"], raw["opacity"], raw["scales"], raw["rotations"], dev)
+    loss_of(out).backward()
+    res.append(({k: v.detach().cpu().numpy() for k, v in out.items()}, {k: torch.nan_to_num(v.grad).cpu().numpy() for k, v in raw.items()}))
+    # (b) reference rasterizer + torch epilogue
+    raw = {k: v.to(dev).clone().requires_grad_(True) for k, v in base.items()}
+    rs = S.settings_for(c, torch.ones(3), 1, dev, reference.GaussianRasterizationSettings)
+    img, radii, allmap = reference.GaussianRasterizer(raster_settings=rs)(
+        means3D=raw["centers"], means2D=torch.zeros_like(raw["centers"], requires_grad=True) + 0, shs=raw["shs"],
+        opacities=torch.sigmoid(raw["opacity"]), scales=torch.exp(raw["scales"]),
+        rotations=torch.nn.functional.normalize(raw["rotations"]), cov3D_precomp=None)
+    out = render_img_epilogue_torch(img, allmap, rays, cam.world_view_transform, 0.0)
+    loss_of(out).backward()
+    res.append(({k: v.detach().cpu().numpy() for k, v in out.items()}, {k: torch.nan_to_num(v.grad).cpu().numpy() for k, v in raw.items()}))
+    (o1, g1), (o2, g2) = res
+    assert sorted(o1) == sorted(o2) == ["acc_map", "depth", "depth_normal", "image", "rend_dist", "rend_normal"]
+    for k in o2:
+        assert o1[k].shape == o2[k].shape
+        assert rel_err(o1[k], o2[k]) < (1e-4 if k == "depth_normal" else 1e-5), k
+    for k in g1:
+        assert np.isfinite(g1[k]).all()
+        assert rel_err(g1[k], g2[k]) < 2e-4, k
