@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRF_ABI_VERSION 1
+#define SRF_ABI_VERSION 2
 
 /* cudaStream_t without pulling in cuda_runtime.h */
 typedef void* srf_stream_t;
@@ -74,7 +74,11 @@ int srf_state_layout(int P, int H, int W, size_t geom_off[3], size_t tile_off[5]
  * event to read it.  `shs` XOR `colors_precomp`, (`scales`,`rotations`) XOR
  * `transMat_precomp` as in the reference (NULL = not given).  scale_modifier and
  * projmatrix are accepted for signature parity and ignored, exactly like the
- * reference (forward.cu:95; auxiliary.h:173-184 only uses the view matrix). */
+ * reference (forward.cu:95; auxiliary.h:173-184 only uses the view matrix).
+ * raw_activations != 0 (next-row extension, no reference counterpart): `opacities`, `scales`,
+ * `rotations` are LaRa's raw network outputs and the kernel applies the activations of
+ * lightning/renderer_2dgs.py:183-188 itself (sigmoid, exp, F.normalize); pass the same flag and
+ * the same raw tensors to srf_backward, whose gradients are then wrt the raw parameters. */
 int srf_forward_preprocess(srf_stream_t stream, int P, int D, int M,
                            const float* means3D, const float* shs, const float* colors_precomp,
                            const float* opacities, const float* scales, float scale_modifier,
@@ -83,7 +87,7 @@ int srf_forward_preprocess(srf_stream_t stream, int P, int D, int M,
                            float tan_fovx, float tan_fovy, int image_height, int image_width,
                            int prefiltered,
                            int* radii, void* geom_state, void* tile_state,
-                           uint32_t* num_rendered_host);
+                           uint32_t* num_rendered_host, int raw_activations);
 
 /* ---- forward, stage 2: tile-bucket scatter, per-tile depth sort, blend ------------
  * Replaces duplicateWithKeys, cub::DeviceRadixSort::SortPairs, identifyTileRanges and
@@ -120,7 +124,8 @@ int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int
                  const float* dL_dout_color, const float* dL_dout_others,
                  void* scratch, int accumulate,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
-                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat);
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                 int raw_activations, const float* opacities_raw);
 
 /* ---- fused render_img epilogue (next-row: lightning/renderer_2dgs.py:220-268, :74-89) ---------
  * One pass over the rasterizer's outputs instead of ~12 torch ops (and ~20 autograd ops):

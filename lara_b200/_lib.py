@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint32, c_void
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsurfel_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/surfel_rasterizer.h one to one
 _P = c_void_p
@@ -36,6 +36,7 @@ SIGNATURES = {
         c_int,                              # prefiltered
         _P, _P, _P,                         # radii, geom_state, tile_state
         _P,                                 # num_rendered_host
+        c_int,                              # raw_activations
     ]),
     "srf_forward_render": (c_int, [
         _P, c_int, c_int, c_int,            # stream, P, H, W
@@ -55,6 +56,7 @@ SIGNATURES = {
         _P, c_int,                               # scratch, accumulate
         _P, _P, _P, _P,                          # dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors
         _P, _P, _P, _P,                          # dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat
+        c_int, _P,                               # raw_activations, opacities_raw
     ]),
     "srf_mark_visible": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "srf_epilogue_forward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -187,7 +187,7 @@ int srf_forward_preprocess(srf_stream_t stream_, int P, int D, int M,
                            const float* viewmatrix, const float* projmatrix, const float* campos,
                            float tan_fovx, float tan_fovy, int image_height, int image_width,
                            int prefiltered, int* radii, void* geom_state, void* tile_state,
-                           uint32_t* num_rendered_host) {
+                           uint32_t* num_rendered_host, int raw_activations) {
     (void)scale_modifier; (void)projmatrix;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_forward_preprocess: bad sizes");
@@ -231,6 +231,7 @@ int srf_forward_preprocess(srf_stream_t stream_, int P, int D, int M,
         a.focal_x = image_width / (2.0f * tan_fovx);
         a.gx = tl.gx; a.gy = tl.gy;
         a.prefiltered = prefiltered;
+        a.raw_act = (raw_activations && !transMat_precomp) ? 1 : 0;
         a.radii = radii;
         a.rec = at<float4>(geom_state, gl.rec);
         a.depths = at<float>(geom_state, gl.depths);
@@ -310,7 +311,8 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
                  const float* dL_dout_color, const float* dL_dout_others,
                  void* scratch, int accumulate,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
-                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat) {
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                 int raw_activations, const float* opacities_raw) {
     (void)projmatrix;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_backward: bad sizes");
@@ -359,6 +361,8 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
     p.tan_fovx = tan_fovx; p.tan_fovy = tan_fovy;
     p.has_precomp_T = transmat_was_precomputed ? 1 : 0;
     p.has_precomp_color = colors_were_precomputed ? 1 : 0;
+    p.raw_act = (raw_activations && !transmat_was_precomputed) ? 1 : 0;
+    p.opacities = opacities_raw;
     p.radii = radii;
     p.rec = r.rec;
     p.ggrad = r.ggrad;

@@ -138,8 +138,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 Tvx = __ldg(t + 3); Tvy = __ldg(t + 4); Tvz = __ldg(t + 5);
                 Twx = __ldg(t + 6); Twy = __ldg(t + 7); Twz = __ldg(t + 8);
             } else {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
-                const float2 sc = __ldg(reinterpret_cast<const float2*>(a.scales) + idx);
+                float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+                float2 sc = __ldg(reinterpret_cast<const float2*>(a.scales) + idx);
+                if (a.raw_act) {       // fused activations: exp on the log-scales, F.normalize on the quaternion
+                    sc.x = expf(sc.x); sc.y = expf(sc.y);
+                    const float n = act_quat_norm(q);
+                    q = make_float4(__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n));
+                }
                 // quat_to_rotmat (auxiliary.h:188-210); glm stores (w,x,y,z) in (.x,.y,.z,.w)
                 const float n2 = fma_(q.z, q.z, fma_(q.y, q.y, fma_(q.w, q.w, fmul_(q.x, q.x))));
                 const float s = rsqrtf(n2);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 rgb[1] = __ldg(a.colors_precomp + (size_t)idx * 3 + 1);
                 rgb[2] = __ldg(a.colors_precomp + (size_t)idx * 3 + 2);
             }
-            const float opac = __ldg(a.opacities + idx);
+            const float opac = a.raw_act ? act_sigmoid(__ldg(a.opacities + idx)) : __ldg(a.opacities + idx);
             // Conservative screen-space *octagon* of the pixels where this splat's alpha can reach
             // 1/255 (the blend's skip threshold): alpha >= 1/255  =>  min(rho3d, rho2d) <= tau with
             // tau = 2 ln(255 opacity).  rho2d <= tau is a disc around the AABB centre; rho3d <= tau

@@ -111,8 +111,15 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             const float fx = a.focal_x, fy = a.focal_y;
             const float cx = a.focal_x * a.tan_fovx, cy = a.focal_y * a.tan_fovy;
 
-            const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
-            const float2 sc = __ldg(reinterpret_cast<const float2*>(a.scales) + idx);
+            const float4 q_in = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+            float4 q = q_in;
+            float2 sc = __ldg(reinterpret_cast<const float2*>(a.scales) + idx);
+            float qn = 1.0f;
+            if (a.raw_act) {
+                sc.x = expf(sc.x); sc.y = expf(sc.y);
+                qn = act_quat_norm(q);
+                q = make_float4(__fdiv_rn(q.x, qn), __fdiv_rn(q.y, qn), __fdiv_rn(q.z, qn), __fdiv_rn(q.w, qn));
+            }
             const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
             const float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
             const V3 R0 = v3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
@@ -156,6 +163,19 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
             drot[3] = 2.f * (x * (vR02 + vR20) + y * (vR12 + vR21) - 2.f * z * (vR00 + vR11) + w * (vR01 - vR10));
             dscale[0] = dot3(dRS[0], R0);
             dscale[1] = dot3(dRS[1], R1);
+            if (a.raw_act) {
+                // vjps of the fused activations: d exp = g * y; d normalize = g/n - x (g.x)/n^3 (n > eps)
+                dscale[0] *= sc.x; dscale[1] *= sc.y;
+                const float gx = drot[0] * q_in.x + drot[1] * q_in.y + drot[2] * q_in.z + drot[3] * q_in.w;
+                const float inv = 1.0f / qn;
+                if (qn > 1e-12f) {
+                    const float k = gx * inv * inv * inv;
+                    drot[0] = drot[0] * inv - q_in.x * k; drot[1] = drot[1] * inv - q_in.y * k;
+                    drot[2] = drot[2] * inv - q_in.z * k; drot[3] = drot[3] * inv - q_in.w * k;
+                } else {
+                    drot[0] *= inv; drot[1] *= inv; drot[2] *= inv; drot[3] *= inv;
+                }
+            }
 
             if (do_sh) {
                 const int clampbits = __float_as_int(q4.w);
@@ -250,6 +270,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         put<ACC>(a.dL_dmeans2D + 3 * (size_t)idx + 0, dmean2D[0]);
         put<ACC>(a.dL_dmeans2D + 3 * (size_t)idx + 1, dmean2D[1]);
         put<ACC>(a.dL_dmeans2D + 3 * (size_t)idx + 2, 0.f);
+    }
+    if (a.raw_act && visible) {            // d sigmoid = g * (1 - y) * y, y = the activated opacity stored in the record
+        const float o = ldg4(a.rec + (size_t)idx * SRF_REC_QUADS + 2).w;
+        dopac = dopac * (1.0f - o) * o;
     }
     put<ACC>(a.dL_dopacity + idx, dopac);
     if (a.vec_ok) {

@@ -122,6 +122,17 @@ __device__ __forceinline__ void tile_pixel(int tid, int& lx, int& ly) {
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// LaRa's activations (lightning/renderer_2dgs.py:106-114, 183-188), in the operation order of
+// torch's CUDA kernels: sigmoid = 1/(1+exp(-x)); exp; F.normalize = x / max(||x||_2, 1e-12).  The
+// 4-element sum of squares is torch 2.11's reduction tree for a contiguous [P,4] tensor,
+// (x0^2+x2^2)+(x1^2+x3^2) (found by bitwise probing on a B200, tools/probe/act_probe.py): with it the
+// fused path is bit-identical to activations-in-torch; another torch build could differ by 1 ulp.
+__device__ __forceinline__ float act_sigmoid(float x) { return __fdiv_rn(1.0f, fadd_(1.0f, expf(-x))); }
+__device__ __forceinline__ float act_quat_norm(float4 q) {
+    const float n = __fsqrt_rn(fadd_(fadd_(fmul_(q.x, q.x), fmul_(q.z, q.z)), fadd_(fmul_(q.y, q.y), fmul_(q.w, q.w))));
+    return fmaxf(n, 1e-12f);
+}
+
 // Pixel-centre bounds of a warp's 8x4 block along x, y, x+y, x-y.
 struct WarpRect {
     float xmin, xmax, ymin, ymax, umin, umax, vmin, vmax;

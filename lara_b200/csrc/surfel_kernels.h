@@ -23,6 +23,7 @@ struct PreprocessArgs {
     int gx, gy;                  // tile grid
     int prefiltered;
     int stage_sh;                // set by the launcher
+    int raw_act;                 // inputs are LaRa's raw network outputs: opacity logits, log-scales, unnormalised quaternions
     int* radii;                  // [P] out
     float4* rec;                 // [P*6] out
     float* depths;               // [P] out
@@ -87,6 +88,8 @@ struct PreprocessBwdArgs {
     float focal_x, focal_y, tan_fovx, tan_fovy;
     int has_precomp_T;           // transMat_precomp was given: only dL_dtransMat is produced
     int has_precomp_color;
+    int raw_act;                 // as in PreprocessArgs; gradients are then wrt the raw parameters
+    const float* opacities;      // raw opacity logits (only read when raw_act)
     const int* radii;
     const float4* rec;
     const float* ggrad;          // [P,20]

@@ -153,7 +153,7 @@ class ForwardState(NamedTuple):
 
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
-                raster_settings: GaussianRasterizationSettings):
+                raster_settings: GaussianRasterizationSettings, raw_activations: bool = False):
     """Enqueue one forward on the current stream of the tensors' device.
 
     Returns (color[3,H,W], allmap[8,H,W], radii[P], ForwardState).  Inputs must already be
@@ -161,10 +161,11 @@ def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tran
     """
     with _DeviceGuard(means3D.device):
         return _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
-                            raster_settings)
+                            raster_settings, raw_activations)
 
 
-def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp, raster_settings):
+def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp, raster_settings,
+                 raw_activations=False):
     lib = _lib.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P = int(means3D.shape[0])
@@ -202,7 +203,7 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
         _ptr(viewm), _ptr(projm), _ptr(campos),
         float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
         1 if raster_settings.prefiltered else 0,
-        radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot.data_ptr()), lib)
+        radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot.data_ptr(), 1 if raw_activations else 0), lib)
     ev = _event(device)
     ev.record()
 
@@ -230,7 +231,8 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
 
 def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scales, rotations,
                  transMat_precomp, raster_settings, grad_color, grad_allmap, *,
-                 out: Optional[dict] = None, accumulate: bool = False, need_means2D: bool = True):
+                 out: Optional[dict] = None, accumulate: bool = False, need_means2D: bool = True,
+                 raw_activations: bool = False, opacities_raw: Optional[torch.Tensor] = None):
     """Enqueue one backward; returns a dict of gradient tensors.
 
     ``out`` may supply pre-allocated (possibly strided-into-a-flat-buffer but contiguous)
@@ -240,11 +242,12 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
     with _DeviceGuard(means3D.device):
         return _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
                              raster_settings, grad_color, grad_allmap, out=out, accumulate=accumulate,
-                             need_means2D=need_means2D)
+                             need_means2D=need_means2D, raw_activations=raw_activations, opacities_raw=opacities_raw)
 
 
 def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
-                  raster_settings, grad_color, grad_allmap, *, out=None, accumulate=False, need_means2D=True):
+                  raster_settings, grad_color, grad_allmap, *, out=None, accumulate=False, need_means2D=True,
+                  raw_activations=False, opacities_raw=None):
     lib = _lib.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P = int(means3D.shape[0])
@@ -284,7 +287,8 @@ def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations,
         grad_color.data_ptr(), grad_allmap.data_ptr(),
         scratch.data_ptr(), 1 if accumulate else 0,
         _ptr(g["means3D"]), _ptr(g["means2D"]), _ptr(g["sh"]), _ptr(g["colors_precomp"]),
-        _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), _ptr(g["cov3Ds_precomp"])), lib)
+        _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), _ptr(g["cov3Ds_precomp"]),
+        1 if raw_activations else 0, _ptr(opacities_raw)), lib)
     if raster_settings.debug:
         torch.cuda.synchronize(device)
     return g
@@ -371,15 +375,18 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 
 
 class _RasterizeGaussians(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+    RAW_ACTIVATIONS = False     # the subclass below flips this: inputs are raw network outputs
+
+    @classmethod
+    def forward(cls, ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                 cov3Ds_precomp, raster_settings):
         raster_settings = _check_settings(raster_settings, means3D.device)
         (means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c) = _normalise_inputs(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         try:
             color, allmap, radii, state = forward_raw(
-                means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings)
+                means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, raster_settings,
+                raw_activations=cls.RAW_ACTIVATIONS)
         except Exception:
             if raster_settings.debug:
                 # same debugging aid as the reference (DSR __init__.py:83-90)
@@ -393,19 +400,21 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.present = (sh_c is not None, colors_c is not None, scales_c is not None,
                        rot_c is not None, cov_c is not None)
         ctx.opac_shape = tuple(opacities.shape)
+        ctx.raw_activations = cls.RAW_ACTIVATIONS
         dummy = means3D_c.new_empty(0)
         ctx.save_for_backward(
             colors_c if colors_c is not None else dummy, means3D_c,
             scales_c if scales_c is not None else dummy, rot_c if rot_c is not None else dummy,
             cov_c if cov_c is not None else dummy, radii, sh_c if sh_c is not None else dummy,
-            state.geom, state.point_list, state.image, state.tile)
+            state.geom, state.point_list, state.image, state.tile,
+            opac_c if cls.RAW_ACTIVATIONS else dummy)
         ctx.mark_non_differentiable(radii)
         return color, radii, allmap
 
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
         rs = ctx.raster_settings
-        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, point_list, image, tile) = ctx.saved_tensors
+        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, point_list, image, tile, opac_raw) = ctx.saved_tensors
         has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
         state = ForwardState(geom, tile, image, point_list, ctx.capacity, ctx.num_rendered)
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
@@ -414,7 +423,9 @@ class _RasterizeGaussians(torch.autograd.Function):
             g = backward_raw(state, radii, means3D,
                              sh if has_sh else None, colors_c if has_col else None,
                              scales if has_sc else None, rotations if has_rot else None,
-                             cov_c if has_cov else None, rs, grad_out_color, grad_depth)
+                             cov_c if has_cov else None, rs, grad_out_color, grad_depth,
+                             raw_activations=ctx.raw_activations,
+                             opacities_raw=opac_raw if ctx.raw_activations else None)
         except Exception:
             if rs.debug:
                 _dump_snapshot("snapshot_bw.dump", (rs, means3D, radii, sh, scales, rotations, grad_out_color, grad_depth))
@@ -425,6 +436,19 @@ class _RasterizeGaussians(torch.autograd.Function):
             g["opacities"] = g["opacities"].view(ctx.opac_shape)
         return (g["means3D"], g["means2D"], g["sh"], g["colors_precomp"], g["opacities"],
                 g["scales"], g["rotations"], g["cov3Ds_precomp"], None)
+
+
+class _RasterizeGaussiansRaw(_RasterizeGaussians):
+    """Same call, but opacities / scales / rotations are LaRa's raw network outputs (logits,
+    log-scales, unnormalised quaternions): the activations of renderer_2dgs.py:183-188 and their
+    vjps run inside the preprocess kernels (next-row extension)."""
+    RAW_ACTIVATIONS = True
+
+
+def rasterize_gaussians_raw(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                            cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussiansRaw.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                        rotations, cov3Ds_precomp, raster_settings)
 
 
 class GaussianRasterizer(nn.Module):
@@ -457,3 +481,14 @@ class GaussianRasterizer(nn.Module):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
                                    rotations, cov3D_precomp, raster_settings)
+
+    def forward_raw_activations(self, means3D, means2D, opacities, scales, rotations, shs=None, colors_precomp=None):
+        """Extension (no reference counterpart): like ``forward`` on the scale/rotation path, but
+        opacities / scales / rotations are LaRa's raw network outputs; sigmoid / exp / F.normalize
+        (renderer_2dgs.py:183-188) and their vjps run inside the preprocess kernels."""
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if scales is None or rotations is None:
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians_raw(means3D, means2D, shs, colors_precomp, opacities, scales,
+                                       rotations, None, self.raster_settings)

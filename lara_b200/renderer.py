@@ -20,8 +20,11 @@ from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
 
 class Renderer(nn.Module):
-    def __init__(self, sh_degree: int = 3, white_background: bool = True, radius: float = 1):
+    def __init__(self, sh_degree: int = 3, white_background: bool = True, radius: float = 1,
+                 fused_activations: bool = True):
         super().__init__()
+        # True: sigmoid / exp / normalize and their vjps run inside the preprocess kernels
+        self.fused_activations = fused_activations
         self.sh_degree = sh_degree
         self.white_background = white_background
         self.radius = radius
@@ -54,20 +57,27 @@ class Renderer(nn.Module):
     def render_img(self, cam, rays, centers, shs, opacity, scales, rotations, device, cov3D_precomp=None,
                    prex: str = "", depth_ratio: float = 0.0):
         rasterizer = self.set_rasterizer(cam, device=device)
-        opacity = self.opacity_activation(opacity)
-        if scales is not None:
-            scales = self.scaling_activation(scales)
-        if rotations is not None:
-            rotations = self.rotation_activation(rotations)
+        fuse = self.fused_activations and cov3D_precomp is None and scales is not None and rotations is not None
+        if not fuse:
+            opacity = self.opacity_activation(opacity)
+            if scales is not None:
+                scales = self.scaling_activation(scales)
+            if rotations is not None:
+                rotations = self.rotation_activation(rotations)
         # gradient sink for the screen-space statistic, as in the reference (:193-206)
         screenspace_points = torch.zeros_like(centers, dtype=centers.dtype, requires_grad=True, device=device) + 0
         try:
             screenspace_points.retain_grad()
         except Exception:
             pass
-        rendered_image, radii, allmap = rasterizer(
-            means3D=centers, means2D=screenspace_points, shs=shs, opacities=opacity, scales=scales,
-            rotations=rotations, cov3D_precomp=cov3D_precomp)
+        if fuse:
+            rendered_image, radii, allmap = rasterizer.forward_raw_activations(
+                means3D=centers, means2D=screenspace_points, shs=shs, opacities=opacity, scales=scales,
+                rotations=rotations)
+        else:
+            rendered_image, radii, allmap = rasterizer(
+                means3D=centers, means2D=screenspace_points, shs=shs, opacities=opacity, scales=scales,
+                rotations=rotations, cov3D_precomp=cov3D_precomp)
         if rays is None:
             return rendered_image.clamp(0, 1)
         return render_img_epilogue(rendered_image, allmap, rays, cam.world_view_transform, depth_ratio, prex)

@@ -62,7 +62,7 @@ def test_bad_arguments_return_status_and_message(lib):
     assert lib.srf_tile_state_bytes(0, 16, ctypes.byref(n)) != 0
     # null / misaligned workspaces are rejected before any CUDA call
     args = [None, 4, 0, 1, None, None, None, None, None, 1.0, None, None, None, None, None,
-            1.0, 1.0, 16, 16, 0, None, None, None, None]
+            1.0, 1.0, 16, 16, 0, None, None, None, None, 0]
     assert lib.srf_forward_preprocess(*args) != 0
     assert lib.srf_last_error() != b""
 

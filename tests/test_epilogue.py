@@ -124,7 +124,48 @@ def test_fused_epilogue_feeds_rasterizer_backward(cuda_device):
 
 
 @pytest.mark.gpu
-def test_fast_renderer_matches_reference_pipeline(cuda_device, reference):
+@pytest.mark.parametrize("sh_degree", [0, 1])
+def test_fused_activations_match_torch_activations(cuda_device, sh_degree):
+    """raw_activations=True (sigmoid / exp / normalize inside the kernels) against the same
+    rasterizer fed with torch's activations: forward bit-identical, raw-parameter gradients 1e-5."""
+    import diff_surfel_rasterization as DSR
+    from lara_b200 import scene as S
+    dev = cuda_device
+    sc = S.scene(40000, 9, sh_degree=sh_degree)
+    cam = S.cameras(1, 160, 192, 2)[0]
+    st = S.settings_for(cam, torch.ones(3), sh_degree, dev, DSR.GaussianRasterizationSettings)
+    base = {"means3D": sc["means3D"], "shs": sc["shs"], "opacities": torch.logit(sc["opacities"].clamp(1e-4, 1 - 1e-4)),
+            "scales": torch.log(sc["scales"]), "rotations": sc["rotations"] * 1.7}
+    g = torch.Generator().manual_seed(3)
+    w_img = torch.randn((3, 160, 192), generator=g).to(dev)
+    w_all = torch.randn((8, 160, 192), generator=g).to(dev)
+    res = []
+    for raw in (True, False):
+        leaves = {k: v.to(dev).clone().requires_grad_(True) for k, v in base.items()}
+        kw = dict(opacities=leaves["opacities"], scales=leaves["scales"], rotations=leaves["rotations"])
+        if not raw:
+            kw = dict(opacities=torch.sigmoid(leaves["opacities"]), scales=torch.exp(leaves["scales"]),
+                      rotations=torch.nn.functional.normalize(leaves["rotations"]))
+        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        rast = DSR.GaussianRasterizer(raster_settings=st)
+        img, radii, allmap = (rast.forward_raw_activations if raw else rast)(
+            means3D=leaves["means3D"], means2D=means2D, shs=leaves["shs"], **kw)
+        ((img * w_img).sum() + (allmap * w_all).sum()).backward()
+        res.append((img.detach().cpu().numpy(), allmap.detach().cpu().numpy(), radii.cpu().numpy(),
+                    {k: v.grad.cpu().numpy() for k, v in leaves.items()}, means2D.grad.cpu().numpy()))
+    a, b = res
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    for k in a[3]:
+        assert np.isfinite(a[3][k]).all(), k
+        assert rel_err(a[3][k], b[3][k]) < 1e-5, k
+    assert rel_err(a[4], b[4]) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused_activations", [True, False])
+def test_fast_renderer_matches_reference_pipeline(cuda_device, reference, fused_activations):
     """lara_b200.renderer.Renderer.render_img == reference rasterizer + the torch epilogue (the
     pipeline LaRa runs today), images and raw-parameter gradients."""
     import types
@@ -151,7 +192,7 @@ def test_fast_renderer_matches_reference_pipeline(cuda_device, reference):
     res = []
     # (a) this repo's fast Renderer
     raw = {k: v.to(dev).clone().requires_grad_(True) for k, v in base.items()}
-    r = Renderer(sh_degree=1, white_background=True)
+    r = Renderer(sh_degree=1, white_background=True, fused_activations=fused_activations)
     out = r.render_img(cam, rays, raw["centers"], raw["shs"], raw["opacity"], raw["scales"], raw["rotations"], dev)
     loss_of(out).backward()
     res.append(({k: v.detach().cpu().numpy() for k, v in out.items()}, {k: torch.nan_to_num(v.grad).cpu().numpy() for k, v in raw.items()}))

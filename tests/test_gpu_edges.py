@@ -30,7 +30,7 @@ def test_empty_scene_returns_zero_images(cuda_device):
     color, radii, allmap = rast(means3D=m3, means2D=torch.zeros_like(m3), shs=scd["shs"], opacities=scd["opacities"],
                                 scales=scd["scales"], rotations=scd["rotations"])
     # reference: zero-filled outputs when P == 0 (rasterize_points.cu:92-105), not background
-    assert float(color.abs().max()) == 0.0 and float(allmap.abs().max()) == 0.0 and radii.numel() == 0
+    assert float(color.detach().abs().max()) == 0.0 and float(allmap.detach().abs().max()) == 0.0 and radii.numel() == 0
     (color.sum() + allmap.sum()).backward()
     assert m3.grad.shape == (0, 3)
 
