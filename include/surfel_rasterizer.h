@@ -112,7 +112,10 @@ int srf_forward_render(srf_stream_t stream, int P, int image_height, int image_w
  * kernel adds into them (used to sum several views before one all-reduce).
  *   dL_dmeans2D[P,3] receives the reference's densification statistic
  *   (backward.cu:645-648), dL_dcolors[P,3] the gradient wrt the (pre-clamp) RGB,
- *   dL_dtransMat[P,9] the gradient wrt the homography (cov3D_precomp slot).          */
+ *   dL_dtransMat[P,9] the gradient wrt the homography (cov3D_precomp slot).
+ * raw_activations: the flag given to srf_forward_preprocess; `scales` / `rotations` are then
+ * the raw tensors and dL_dopacity / dL_dscales / dL_drotations are wrt the raw parameters
+ * (the activated opacity is read back from geom_state).                               */
 int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int image_width,
                  size_t capacity, const float* background,
                  const float* means3D, const float* shs, int colors_were_precomputed,
@@ -125,7 +128,7 @@ int srf_backward(srf_stream_t stream, int P, int D, int M, int image_height, int
                  void* scratch, int accumulate,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
-                 int raw_activations, const float* opacities_raw);
+                 int raw_activations);
 
 /* ---- fused render_img epilogue (next-row: lightning/renderer_2dgs.py:220-268, :74-89) ---------
  * One pass over the rasterizer's outputs instead of ~12 torch ops (and ~20 autograd ops):

@@ -56,7 +56,7 @@ SIGNATURES = {
         _P, c_int,                               # scratch, accumulate
         _P, _P, _P, _P,                          # dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors
         _P, _P, _P, _P,                          # dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat
-        c_int, _P,                               # raw_activations, opacities_raw
+        c_int,                                   # raw_activations
     ]),
     "srf_mark_visible": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "srf_epilogue_forward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -312,7 +312,7 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
                  void* scratch, int accumulate,
                  float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
-                 int raw_activations, const float* opacities_raw) {
+                 int raw_activations) {
     (void)projmatrix;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || image_height <= 0 || image_width <= 0) return fail("srf_backward: bad sizes");
@@ -362,7 +362,6 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
     p.has_precomp_T = transmat_was_precomputed ? 1 : 0;
     p.has_precomp_color = colors_were_precomputed ? 1 : 0;
     p.raw_act = (raw_activations && !transmat_was_precomputed) ? 1 : 0;
-    p.opacities = opacities_raw;
     p.radii = radii;
     p.rec = r.rec;
     p.ggrad = r.ggrad;

@@ -89,7 +89,6 @@ struct PreprocessBwdArgs {
     int has_precomp_T;           // transMat_precomp was given: only dL_dtransMat is produced
     int has_precomp_color;
     int raw_act;                 // as in PreprocessArgs; gradients are then wrt the raw parameters
-    const float* opacities;      // raw opacity logits (only read when raw_act)
     const int* radii;
     const float4* rec;
     const float* ggrad;          // [P,20]

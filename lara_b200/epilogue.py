@@ -32,10 +32,37 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.contiguous()
 
 
+def epilogue_forward_raw(color, allmap, rays, viewmatrix, depth_ratio, image, depth, acc, rn, dn, dist):
+    """Enqueue the fused forward on the current stream; all tensors contiguous fp32 on one device,
+    outputs planar ([3,H,W], [1,H,W], [H,W], [3,H,W], [3,H,W], [H,W]; slices of stacked buffers are fine)."""
+    lib = _lib.load()
+    H, W = int(color.shape[1]), int(color.shape[2])
+    dev = color.device
+    with _DeviceGuard(dev):
+        _lib.check(lib.srf_epilogue_forward(
+            _raw_stream(dev), H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays),
+            viewmatrix.data_ptr(), image.data_ptr(), depth.data_ptr(), acc.data_ptr(), rn.data_ptr(),
+            dn.data_ptr(), dist.data_ptr()), lib)
+
+
+def epilogue_backward_raw(color, allmap, rays, viewmatrix, depth_ratio, gi, gd, ga, grn, gdn, gds):
+    """Enqueue the fused backward; upstream gradients may be None.  Returns (dL_dcolor[3,H,W], dL_dallmap[8,H,W])."""
+    lib = _lib.load()
+    H, W = int(color.shape[1]), int(color.shape[2])
+    dev = color.device
+    buf = torch.empty((14, H, W), dtype=torch.float32, device=dev)
+    scratch, d_color, d_allmap = buf[0:3], buf[3:6], buf[6:14]
+    with _DeviceGuard(dev):
+        _lib.check(lib.srf_epilogue_backward(
+            _raw_stream(dev), H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays),
+            viewmatrix.data_ptr(), _p(gi), _p(gd), _p(ga), _p(grn), _p(gdn), _p(gds),
+            scratch.data_ptr(), d_color.data_ptr(), d_allmap.data_ptr()), lib)
+    return d_color, d_allmap
+
+
 class _Epilogue(torch.autograd.Function):
     @staticmethod
     def forward(ctx, color, allmap, rays, viewmatrix, depth_ratio):
-        lib = _lib.load()
         color = color.contiguous(); allmap = allmap.contiguous()
         viewmatrix = viewmatrix.contiguous()
         rays_c = rays.contiguous() if rays is not None else None
@@ -48,11 +75,7 @@ class _Epilogue(torch.autograd.Function):
         # separate planar tensors; the [H,W,C] permutes happen outside the Function so that the
         # results are ordinary autograd views (callers may then modify them in place)
         image, depth, acc, rn, dn, dist = new(3, H, W), new(1, H, W), new(H, W), new(3, H, W), new(3, H, W), new(H, W)
-        with _DeviceGuard(dev):
-            _lib.check(lib.srf_epilogue_forward(
-                _raw_stream(dev), H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays_c),
-                viewmatrix.data_ptr(), image.data_ptr(), depth.data_ptr(), acc.data_ptr(), rn.data_ptr(),
-                dn.data_ptr(), dist.data_ptr()), lib)
+        epilogue_forward_raw(color, allmap, rays_c, viewmatrix, depth_ratio, image, depth, acc, rn, dn, dist)
         ctx.save_for_backward(color, allmap, rays_c if rays_c is not None else color.new_empty(0), viewmatrix)
         ctx.has_rays = rays_c is not None
         ctx.depth_ratio = float(depth_ratio)
@@ -60,19 +83,10 @@ class _Epilogue(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_image, g_depth, g_acc, g_rn, g_dn, g_dist):
-        lib = _lib.load()
         color, allmap, rays, viewmatrix = ctx.saved_tensors
         rays = rays if ctx.has_rays else None
-        H, W = int(color.shape[1]), int(color.shape[2])
-        dev = color.device
-        gi, gd, ga, grn, gdn, gds = _c(g_image), _c(g_depth), _c(g_acc), _c(g_rn), _c(g_dn), _c(g_dist)
-        buf = torch.empty((14, H, W), dtype=torch.float32, device=dev)
-        scratch, d_color, d_allmap = buf[0:3], buf[3:6], buf[6:14]
-        with _DeviceGuard(dev):
-            _lib.check(lib.srf_epilogue_backward(
-                _raw_stream(dev), H, W, ctx.depth_ratio, color.data_ptr(), allmap.data_ptr(), _p(rays),
-                viewmatrix.data_ptr(), _p(gi), _p(gd), _p(ga), _p(grn), _p(gdn), _p(gds),
-                scratch.data_ptr(), d_color.data_ptr(), d_allmap.data_ptr()), lib)
+        d_color, d_allmap = epilogue_backward_raw(color, allmap, rays, viewmatrix, ctx.depth_ratio, _c(g_image), _c(g_depth),
+                                                  _c(g_acc), _c(g_rn), _c(g_dn), _c(g_dist))
         return d_color, d_allmap, None, None, None
 
 

@@ -232,7 +232,7 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
 def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scales, rotations,
                  transMat_precomp, raster_settings, grad_color, grad_allmap, *,
                  out: Optional[dict] = None, accumulate: bool = False, need_means2D: bool = True,
-                 raw_activations: bool = False, opacities_raw: Optional[torch.Tensor] = None):
+                 raw_activations: bool = False):
     """Enqueue one backward; returns a dict of gradient tensors.
 
     ``out`` may supply pre-allocated (possibly strided-into-a-flat-buffer but contiguous)
@@ -242,12 +242,12 @@ def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scale
     with _DeviceGuard(means3D.device):
         return _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
                              raster_settings, grad_color, grad_allmap, out=out, accumulate=accumulate,
-                             need_means2D=need_means2D, raw_activations=raw_activations, opacities_raw=opacities_raw)
+                             need_means2D=need_means2D, raw_activations=raw_activations)
 
 
 def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
                   raster_settings, grad_color, grad_allmap, *, out=None, accumulate=False, need_means2D=True,
-                  raw_activations=False, opacities_raw=None):
+                  raw_activations=False):
     lib = _lib.load()
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P = int(means3D.shape[0])
@@ -288,7 +288,7 @@ def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations,
         scratch.data_ptr(), 1 if accumulate else 0,
         _ptr(g["means3D"]), _ptr(g["means2D"]), _ptr(g["sh"]), _ptr(g["colors_precomp"]),
         _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), _ptr(g["cov3Ds_precomp"]),
-        1 if raw_activations else 0, _ptr(opacities_raw)), lib)
+        1 if raw_activations else 0), lib)
     if raster_settings.debug:
         torch.cuda.synchronize(device)
     return g
@@ -406,15 +406,14 @@ class _RasterizeGaussians(torch.autograd.Function):
             colors_c if colors_c is not None else dummy, means3D_c,
             scales_c if scales_c is not None else dummy, rot_c if rot_c is not None else dummy,
             cov_c if cov_c is not None else dummy, radii, sh_c if sh_c is not None else dummy,
-            state.geom, state.point_list, state.image, state.tile,
-            opac_c if cls.RAW_ACTIVATIONS else dummy)
+            state.geom, state.point_list, state.image, state.tile)
         ctx.mark_non_differentiable(radii)
         return color, radii, allmap
 
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
         rs = ctx.raster_settings
-        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, point_list, image, tile, opac_raw) = ctx.saved_tensors
+        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, point_list, image, tile) = ctx.saved_tensors
         has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
         state = ForwardState(geom, tile, image, point_list, ctx.capacity, ctx.num_rendered)
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
@@ -424,8 +423,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                              sh if has_sh else None, colors_c if has_col else None,
                              scales if has_sc else None, rotations if has_rot else None,
                              cov_c if has_cov else None, rs, grad_out_color, grad_depth,
-                             raw_activations=ctx.raw_activations,
-                             opacities_raw=opac_raw if ctx.raw_activations else None)
+                             raw_activations=ctx.raw_activations)
         except Exception:
             if rs.debug:
                 _dump_snapshot("snapshot_bw.dump", (rs, means3D, radii, sh, scales, rotations, grad_out_color, grad_depth))

@@ -81,3 +81,23 @@ class Renderer(nn.Module):
         if rays is None:
             return rendered_image.clamp(0, 1)
         return render_img_epilogue(rendered_image, allmap, rays, cam.world_view_transform, depth_ratio, prex)
+
+    def render_views(self, cams, rays, centers, shs, opacity, scales, rotations, device, bg_colors=None,
+                     prex: str = "", depth_ratio: float = 0.0, streams: int = 3):
+        """All target views of one scene in one autograd node (the loop of network.py:486-495):
+        ``cams`` a sequence of MiniCam-like objects, ``rays`` [V,H,W,6] (or None), ``bg_colors`` an
+        optional [V,3] / sequence of per-view backgrounds (network.py:489-490), default ``self.bg_color``.
+        Returns stacked ``{key: [V,H,W,C]}``; ``lara_b200.multiview.concat_views`` gives network.py:525's layout."""
+        from .multiview import render_scene_views
+        settings = []
+        for j, cam in enumerate(cams):
+            if bg_colors is not None:
+                self.set_bg_color(bg_colors[j])
+            settings.append(self.set_rasterizer(cam, device=device).raster_settings)
+        fuse = self.fused_activations
+        if not fuse:
+            opacity = self.opacity_activation(opacity)
+            scales = self.scaling_activation(scales)
+            rotations = self.rotation_activation(rotations)
+        return render_scene_views(centers, shs, opacity, scales, rotations, settings, rays=rays, depth_ratio=depth_ratio,
+                                  raw_activations=fuse, streams=streams, prex=prex)
