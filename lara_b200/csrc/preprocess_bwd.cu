@@ -68,15 +68,16 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         const float4 q0 = ldg4(r), q1 = ldg4(r + 1), q2 = ldg4(r + 2), q4 = ldg4(r + 4);
         const float4* gq = reinterpret_cast<const float4*>(a.ggrad + (size_t)idx * SRF_GRAD_FLOATS);
         const float4 g0 = ldg4(gq), g1 = ldg4(gq + 1), g2 = ldg4(gq + 2), g3 = ldg4(gq + 3), g4 = ldg4(gq + 4);
-        dT[0] = g0.x; dT[1] = g0.y; dT[2] = g0.z; dT[3] = g0.w;
-        dT[4] = g1.x; dT[5] = g1.y; dT[6] = g1.z; dT[7] = g1.w;
+        // record slots 0..5 hold (dk.x, -dl.x, dk.y, -dl.y, dk.z, -dl.z); dL_dTu = -dk, dL_dTv = -dl
+        dT[0] = -g0.x; dT[3] = g0.y; dT[1] = -g0.z; dT[4] = g0.w;
+        dT[2] = -g1.x; dT[5] = g1.y; dT[6] = g1.z; dT[7] = g1.w;
         dT[8] = g2.x;
         const float dmx = g2.y, dmy = g2.z;
         dopac = g2.w;
         const float dnx = g3.x, dny = g3.y, dnz = g3.z;
         dcol[0] = g3.w; dcol[1] = g4.x; dcol[2] = g4.y;
 
-        const V3 Tu = v3(q0.x, q0.y, q0.z), Tv = v3(q0.w, q1.x, q1.y), Tw = v3(q1.z, q1.w, q2.x);
+        const V3 Tu = v3(q0.x, q0.z, q1.x), Tv = v3(q0.y, q0.w, q1.y), Tw = v3(q1.z, q1.w, q2.x);
 
         // ---- K8: AABB-centre vjp (backward.cu:599-649)
         {

@@ -19,6 +19,14 @@
 
 namespace srf {
 
+// MUFU.RCP, <= 1 ulp: the gradients need no bit-exactness (the forward-deciding chain in eval_pair()
+// keeps its IEEE divisions), and an IEEE reciprocal costs ~9 instructions plus a slow-path call.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
@@ -140,11 +148,14 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
     for (int w = 0; w < 8; ++w) n_eff = max(n_eff, s_wmax[w]);
     const int rounds = (n_eff + 255) >> 8;
 
-    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;        // accum_rec
-    float last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;     // last_color
-    float last_alpha = 0.f, last_depth = 0.f;
-    float last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f;
-    float acc_depth = 0.f, acc_alpha = 0.f, acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
+    // accum_rec / last_* recursions of backward.cu:331-385, two channels per packed fp32x2 register:
+    // (c0,c1) (c2,depth) (n0,n1) (n2,alpha); the matching upstream gradients are paired the same way
+    f32x2 acc_c01 = 0ull, acc_c2d = 0ull, acc_n01 = 0ull, acc_n2a = 0ull;
+    f32x2 last_c01 = 0ull, last_c2d = 0ull, last_n01 = 0ull, last_n2a = 0ull;
+    float last_alpha = 0.f;
+    const f32x2 dpix01 = pk2(dpix0, dpix1), dpix2d = pk2(dpix2, dL_ddepth);
+    const f32x2 dn01 = pk2(dn0, dn1), dn2a = pk2(dn2, dL_daccum);
+    const float npixy = -pixy;
     float last_dL_dT = 0.f;
 
     for (int b = 0; b < rounds; ++b) {
@@ -204,27 +215,35 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
                 const float opac = q2.w;
 
                 // one reciprocal serves T / (1-alpha) and the background term's T_final / (1-alpha)
-                const float r1ma = __frcp_rn(1.0f - alpha);
+                const float r1ma = rcp_fast(1.0f - alpha);   // 1 - alpha >= 0.01
                 T = T * r1ma;
                 const float w = alpha * T;  // dchannel_dcolor
-                float dL_dalpha = 0.0f;
-                // colour (backward.cu:331-346)
-                acc_c0 = last_alpha * last_c0 + (1.f - last_alpha) * acc_c0; last_c0 = q4.x;
-                acc_c1 = last_alpha * last_c1 + (1.f - last_alpha) * acc_c1; last_c1 = q4.y;
-                acc_c2 = last_alpha * last_c2 + (1.f - last_alpha) * acc_c2; last_c2 = q4.z;
-                dL_dalpha += (q4.x - acc_c0) * dpix0;
-                dL_dalpha += (q4.y - acc_c1) * dpix1;
-                dL_dalpha += (q4.z - acc_c2) * dpix2;
-                g[SRF_G_DCOLOR + 0] = w * dpix0;
-                g[SRF_G_DCOLOR + 1] = w * dpix1;
-                g[SRF_G_DCOLOR + 2] = w * dpix2;
+                // accum_rec <- last_alpha * last + (1 - last_alpha) * accum_rec  (all eight channels)
+                const f32x2 la2 = bc2(last_alpha), oma2 = bc2(1.0f - last_alpha);
+                acc_c01 = fma2(last_c01, la2, mul2(acc_c01, oma2));
+                acc_c2d = fma2(last_c2d, la2, mul2(acc_c2d, oma2));
+                acc_n01 = fma2(last_n01, la2, mul2(acc_n01, oma2));
+                acc_n2a = fma2(last_n2a, la2, mul2(acc_n2a, oma2));
+                last_c01 = pk2(q4.x, q4.y); last_c2d = pk2(q4.z, c_d);
+                last_n01 = pk2(q3.x, q3.y); last_n2a = pk2(q3.z, 1.0f);
+                // dL_dalpha += (channel - accum_rec) * dL_dchannel over colour, depth, normal, alpha
+                f32x2 dsum = mul2(sub2(last_c01, acc_c01), dpix01);
+                dsum = fma2(sub2(last_c2d, acc_c2d), dpix2d, dsum);
+                dsum = fma2(sub2(last_n01, acc_n01), dn01, dsum);
+                dsum = fma2(sub2(last_n2a, acc_n2a), dn2a, dsum);
+                const float2 dsum_ = up2(dsum);
+                // w * upstream: colour and normal gradients of the splat, and w * dL_ddepth for dL_dz
+                const f32x2 w2 = bc2(w);
+                const float2 gc01 = up2(mul2(dpix01, w2)), gc2d = up2(mul2(dpix2d, w2)), gn01 = up2(mul2(dn01, w2));
+                g[SRF_G_DCOLOR + 0] = gc01.x; g[SRF_G_DCOLOR + 1] = gc01.y; g[SRF_G_DCOLOR + 2] = gc2d.x;
+                g[SRF_G_DNORMAL + 0] = gn01.x; g[SRF_G_DNORMAL + 1] = gn01.y; g[SRF_G_DNORMAL + 2] = w * dn2;
 
-                float dL_dz = 0.0f, dL_dweight = 0.0f;
+                float dL_dz = gc2d.y, dL_dweight = 0.0f;
                 // distortion / median terms (backward.cu:350-368).  m_d = (FAR d - FAR NEAR)/((FAR-NEAR) d)
                 // = c1 - c2/d and d m_d/dd = c2/d^2; the reference evaluates both in double.  fp32 is
                 // enough here: the weight term below is stationary in m_d (its derivative is
                 // 2 (m_d A - D) ~ 0), and the gradients carry 1e-6 atomic-order noise anyway.
-                const float rcd = __frcp_rn(c_d);
+                const float rcd = rcp_fast(c_d);             // depth >= 0.2
                 const float m_d = fmaf(-(float)(20.0 / 99.8), rcd, (float)(100.0 / 99.8));
                 const float dmd_dd = (float)(20.0 / 99.8) * rcd * rcd;
                 if (pos == median_contributor - 1) {
@@ -232,25 +251,10 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
                     dL_dweight += dL_dmax_dweight;
                 }
                 dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
-                dL_dalpha += dL_dweight - last_dL_dT;
+                float dL_dalpha = (dsum_.x + dsum_.y) + (dL_dweight - last_dL_dT);
                 last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
-                const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
                 dL_dz += dL_dmd * dmd_dd;
-                // depth / alpha / normal maps (backward.cu:370-385)
-                acc_depth = last_alpha * last_depth + (1.f - last_alpha) * acc_depth;
-                last_depth = c_d;
-                dL_dalpha += (c_d - acc_depth) * dL_ddepth;
-                acc_alpha = last_alpha * 1.0f + (1.f - last_alpha) * acc_alpha;
-                dL_dalpha += (1.0f - acc_alpha) * dL_daccum;
-                acc_n0 = last_alpha * last_n0 + (1.f - last_alpha) * acc_n0; last_n0 = q3.x;
-                acc_n1 = last_alpha * last_n1 + (1.f - last_alpha) * acc_n1; last_n1 = q3.y;
-                acc_n2 = last_alpha * last_n2 + (1.f - last_alpha) * acc_n2; last_n2 = q3.z;
-                dL_dalpha += (q3.x - acc_n0) * dn0;
-                dL_dalpha += (q3.y - acc_n1) * dn1;
-                dL_dalpha += (q3.z - acc_n2) * dn2;
-                g[SRF_G_DNORMAL + 0] = w * dn0;
-                g[SRF_G_DNORMAL + 1] = w * dn1;
-                g[SRF_G_DNORMAL + 2] = w * dn2;
 
                 dL_dalpha *= T;
                 last_alpha = alpha;
@@ -258,34 +262,33 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
                 dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
 
                 const float dL_dG = opac * dL_dalpha;
-                dL_dz += w * dL_ddepth;
 
                 if (e.rho3d <= e.rho2d) {
                     // ray-splat branch: vjp through s = p.xy / p.z, p = k x l (backward.cu:405-435)
-                    const float dL_dsx = dL_dG * -G * e.sx + dL_dz * Twx;
-                    const float dL_dsy = dL_dG * -G * e.sy + dL_dz * Twy;
-                    const float rpz = __frcp_rn(e.pz);
-                    const float dsx_pz = dL_dsx * rpz;
-                    const float dsy_pz = dL_dsy * rpz;
-                    const float dpx = dsx_pz, dpy = dsy_pz, dpz = -(dsx_pz * e.sx + dsy_pz * e.sy);
-                    // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
-                    const float dkx = e.ly * dpz - e.lz * dpy;
-                    const float dky = e.lz * dpx - e.lx * dpz;
-                    const float dkz = e.lx * dpy - e.ly * dpx;
-                    const float dlx = dpy * e.kz - dpz * e.ky;
-                    const float dly = dpz * e.kx - dpx * e.kz;
-                    const float dlz = dpx * e.ky - dpy * e.kx;
-                    g[SRF_G_DT + 0] = -dkx; g[SRF_G_DT + 1] = -dky; g[SRF_G_DT + 2] = -dkz;
-                    g[SRF_G_DT + 3] = -dlx; g[SRF_G_DT + 4] = -dly; g[SRF_G_DT + 5] = -dlz;
-                    g[SRF_G_DT + 6] = pixx * dkx + pixy * dlx + dL_dz * e.sx;
-                    g[SRF_G_DT + 7] = pixx * dky + pixy * dly + dL_dz * e.sy;
-                    g[SRF_G_DT + 8] = pixx * dkz + pixy * dlz + dL_dz;
+                    const f32x2 S = pk2(e.sx, e.sy);
+                    const f32x2 dS = fma2(S, bc2(dL_dG * -G), mul2(pk2(Twx, Twy), bc2(dL_dz)));   // (dL_dsx, dL_dsy)
+                    const f32x2 dPxy = mul2(dS, bc2(rcp_fast(e.pz)));                           // (dL_dpx, dL_dpy)
+                    const float2 dp = up2(dPxy), dps = up2(mul2(dPxy, S));
+                    const float dpz = -(dps.x + dps.y);
+                    // dL_dk = l x dL_dp, dL_dl = dL_dp x k, as the pairs (dk.c, -dl.c) = the gradient record's layout:
+                    //   (dk.x,-dl.x) = (l.y,k.y) dpz - (l.z,k.z) dpy   and cyclic
+                    const f32x2 Sx = pk2(e.lx, e.kx), Sy = pk2(e.ly, e.ky), Sz = pk2(e.lz, e.kz);
+                    const float2 Dx = up2(fma2(Sy, bc2(dpz), mul2(Sz, bc2(-dp.y))));
+                    const float2 Dy = up2(fma2(Sz, bc2(dp.x), mul2(Sx, bc2(-dpz))));
+                    const float2 Dz = up2(fma2(Sx, bc2(dp.y), mul2(Sy, bc2(-dp.x))));
+                    g[SRF_G_DT + 0] = Dx.x; g[SRF_G_DT + 1] = Dx.y;
+                    g[SRF_G_DT + 2] = Dy.x; g[SRF_G_DT + 3] = Dy.y;
+                    g[SRF_G_DT + 4] = Dz.x; g[SRF_G_DT + 5] = Dz.y;
+                    // dL_dTw = pix.x dk + pix.y dl + dL_dz (s, 1)
+                    const float2 zs = up2(mul2(S, bc2(dL_dz)));
+                    g[SRF_G_DT + 6] = fmaf(pixx, Dx.x, fmaf(npixy, Dx.y, zs.x));
+                    g[SRF_G_DT + 7] = fmaf(pixx, Dy.x, fmaf(npixy, Dy.y, zs.y));
+                    g[SRF_G_DT + 8] = fmaf(pixx, Dz.x, fmaf(npixy, Dz.y, dL_dz));
                 } else {
                     // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
-                    const float dG_ddelx = -G * 2.0f * e.dx;
-                    const float dG_ddely = -G * 2.0f * e.dy;
-                    g[SRF_G_DMEAN2D + 0] = dL_dG * dG_ddelx;
-                    g[SRF_G_DMEAN2D + 1] = dL_dG * dG_ddely;
+                    const float2 gm = up2(mul2(pk2(e.dx, e.dy), bc2(dL_dG * (-2.0f * G))));
+                    g[SRF_G_DMEAN2D + 0] = gm.x;
+                    g[SRF_G_DMEAN2D + 1] = gm.y;
                     g[SRF_G_DT + 8] = dL_dz;
                 }
                 g[SRF_G_DOPAC] = G * dL_dalpha;

@@ -36,9 +36,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     bool done = !inside;
     float T = 1.0f;
     uint32_t contributor = 0, last_contributor = 0;
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    float D = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
-    float dist1 = 0.f, dist2 = 0.f, distortion = 0.f;
+    // accumulators, two per packed fp32x2 register: (C0,C1) (C2,distortion) (N0,N1) (N2,D) (dist1,dist2)
+    f32x2 C01 = 0ull, C2r = 0ull, N01 = 0ull, N2D = 0ull, d12 = 0ull;
     float median_depth = 0.f, median_weight = 0.f;
     // 1-based list position of the median contributor, 0 = none.  (The reference keeps a float
     // initialised to -1 and converts it to u32 at the end -- 0 after saturation; for tiles with an
@@ -95,28 +94,30 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             const float A = fadd_(1.0f, -T);
             const float m = mapped_depth(depth);
             const float mm = fmul_(m, m);
-            const float err = fma_(-dist1, fadd_(m, m), fma_(A, mm, dist2));
-            distortion = fma_(T, fmul_(alpha, err), distortion);
+            const float2 d12_ = up2(d12);
+            const float err = fma_(-d12_.x, fadd_(m, m), fma_(A, mm, d12_.y));
             if (T > 0.5f) {
                 median_depth = depth;
                 median_weight = fmul_(T, alpha);
                 median_contributor = contributor;
             }
-            N0 = fma_(T, fmul_(q3.x, alpha), N0);
-            N1 = fma_(T, fmul_(q3.y, alpha), N1);
-            N2 = fma_(T, fmul_(q3.z, alpha), N2);
-            D = fma_(T, fmul_(depth, alpha), D);
-            dist1 = fma_(T, fmul_(alpha, m), dist1);
-            dist2 = fma_(T, fmul_(alpha, mm), dist2);
-            C0 = fma_(T, fmul_(alpha, q4.x), C0);
-            C1 = fma_(T, fmul_(alpha, q4.y), C1);
-            C2 = fma_(T, fmul_(alpha, q4.z), C2);
+            // every channel: acc = fma(T, channel * alpha, acc) -- the reference's rounding sequence,
+            // two channels per FMUL2 / FFMA2
+            const f32x2 a2 = bc2(alpha), T2 = bc2(T);
+            C01 = fma2(T2, mul2(pk2(q4.x, q4.y), a2), C01);
+            C2r = fma2(T2, mul2(pk2(q4.z, err), a2), C2r);
+            N01 = fma2(T2, mul2(pk2(q3.x, q3.y), a2), N01);
+            N2D = fma2(T2, mul2(pk2(q3.z, depth), a2), N2D);
+            d12 = fma2(T2, mul2(pk2(m, mm), a2), d12);
             T = test_T;
             last_contributor = contributor;
           }
         }
     }
 
+    const float2 C01_ = up2(C01), C2r_ = up2(C2r), N01_ = up2(N01), N2D_ = up2(N2D), d12_f = up2(d12);
+    const float C0 = C01_.x, C1 = C01_.y, C2 = C2r_.x, distortion = C2r_.y;
+    const float N0 = N01_.x, N1 = N01_.y, N2 = N2D_.x, D = N2D_.y, dist1 = d12_f.x, dist2 = d12_f.y;
     if (inside) {
         const size_t npix = (size_t)a.W * a.H;
         const size_t pix = (size_t)pyi * a.W + pxi;

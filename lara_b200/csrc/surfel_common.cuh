@@ -5,8 +5,8 @@
 //
 //   GeomRecord  : 6 x float4 = 96 B per Gaussian, record-major, 32 B aligned so one
 //                 gather touches exactly three DRAM sectors.
-//       q0 = Tu.x Tu.y Tu.z Tv.x          (rows of the splat->screen homography T,
-//       q1 = Tv.y Tv.z Tw.x Tw.y           reference forward.cu:75-128)
+//       q0 = Tu.x Tv.x Tu.y Tv.y          (rows of the splat->screen homography T, reference
+//       q1 = Tu.z Tv.z Tw.x Tw.y           forward.cu:75-128; Tu/Tv interleaved = fp32x2 operands)
 //       q2 = Tw.z cx   cy   opacity       (cx,cy = screen-space AABB centre)
 //       q3 = n.x  n.y  n.z  depth         (view-space normal, view-space z)
 //       q4 = r    g    b    clamp-bits    (SH->RGB colour, 3 clamp flags as int bits)
@@ -29,7 +29,7 @@
 #define SRF_GRAD_FLOATS 20  // per-Gaussian gradient accumulation record (5 x float4)
 
 // gradient accumulation record layout (floats)
-#define SRF_G_DT 0        // 9: dL/dT
+#define SRF_G_DT 0        // 9: (dk.x, -dl.x, dk.y, -dl.y, dk.z, -dl.z) = (-dL/dTu, dL/dTv) interleaved, then dL/dTw
 #define SRF_G_DMEAN2D 9   // 2: dL/dmean2D (low-pass branch)
 #define SRF_G_DOPAC 11    // 1
 #define SRF_G_DNORMAL 12  // 3
@@ -47,6 +47,18 @@
 __device__ __forceinline__ float fmul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd_(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two IEEE fp32 operations per lane in
+// one issue slot; ptxas folds broadcast, lane-swap and negation of an operand into the instruction).
+// The blend kernels are issue-bound, so pairing independent fp32 operations is what buys time.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ float2 up2(f32x2 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // Result of intersecting one pixel ray with one splat (reference forward.cu:353-398,
 // backward.cu:258-318).  `valid` is false when the reference would `continue`.
@@ -66,20 +78,19 @@ struct PairEval {
 //   q0,q1,q2 : first three quads of the GeomRecord.
 __device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, const float4 q2,
                                           const float pixx, const float pixy, PairEval& e) {
-    const float Tux = q0.x, Tuy = q0.y, Tuz = q0.z;
-    const float Tvx = q0.w, Tvy = q1.x, Tvz = q1.y;
     const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
-    const float cx = q2.y, cy = q2.z, opac = q2.w;
+    const float opac = q2.w;
     // Straight-line code: the reference `continue`s at five places, but within a warp those
     // early-outs almost never agree, so the rejection tests are folded into one predicate at the
     // end (division by p.z == 0 just yields inf/NaN, which the predicate discards).
     // k = pix.x * Tw - Tu ; l = pix.y * Tw - Tv
-    e.kx = fma_(pixx, Twx, -Tux);
-    e.ky = fma_(pixx, Twy, -Tuy);
-    e.kz = fma_(pixx, Twz, -Tuz);
-    e.lx = fma_(pixy, Twx, -Tvx);
-    e.ly = fma_(pixy, Twy, -Tvy);
-    e.lz = fma_(pixy, Twz, -Tvz);
+    // -- as three packed FFMA2: (k.c, l.c) = (pix.x, pix.y) * Tw.c - (Tu.c, Tv.c); each lane is the same
+    // single-rounding fma as the scalar form, so the results are bit-identical
+    const f32x2 pix2 = pk2(pixx, pixy);
+    const float2 klx = up2(fma2(pix2, bc2(Twx), pk2(-q0.x, -q0.y)));
+    const float2 kly = up2(fma2(pix2, bc2(Twy), pk2(-q0.z, -q0.w)));
+    const float2 klz = up2(fma2(pix2, bc2(Twz), pk2(-q1.x, -q1.y)));
+    e.kx = klx.x; e.lx = klx.y; e.ky = kly.x; e.ly = kly.y; e.kz = klz.x; e.lz = klz.y;
     // p = k x l, each component fma(a,b,-(c*d))
     e.pz = fma_(e.kx, e.ly, -fmul_(e.ky, e.lx));
     e.px = fma_(e.ky, e.lz, -fmul_(e.kz, e.ly));
@@ -87,8 +98,8 @@ __device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, cons
     e.sx = __fdiv_rn(e.px, e.pz);
     e.sy = __fdiv_rn(e.py, e.pz);
     e.rho3d = fma_(e.sx, e.sx, fmul_(e.sy, e.sy));
-    e.dx = fadd_(cx, -pixx);
-    e.dy = fadd_(cy, -pixy);
+    const float2 dxy = up2(sub2(pk2(q2.y, q2.z), pix2));      // centre - pixel
+    e.dx = dxy.x; e.dy = dxy.y;
     // FilterInvSquare * |d|^2 is evaluated in double by the reference; the double
     // constant 1/(0.70710678118654762)^2 rounds the product to exactly 2*|d|^2 in fp32.
     e.rho2d = fmul_(2.0f, fma_(e.dx, e.dx, fmul_(e.dy, e.dy)));

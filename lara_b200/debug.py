@@ -25,7 +25,7 @@ def unpack_state(state: ForwardState, P: int, H: int, W: int) -> Dict[str, torch
     if P > 0:
         rec = state.geom[g_off[0]:g_off[0] + 96 * P].view(torch.float32).view(P, 24)
         out["rec"] = rec
-        out["transMat"] = rec[:, 0:9]
+        out["transMat"] = rec[:, [0, 2, 4, 1, 3, 5, 6, 7, 8]]     # record interleaves Tu / Tv (surfel_common.cuh)
         out["means2D"] = rec[:, 9:11]
         out["opacity"] = rec[:, 11]
         out["normal"] = rec[:, 12:15]
