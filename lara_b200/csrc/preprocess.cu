@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                     const float rz[4] = {Tuz, Tvz, Tuz + Tvz, Tuz - Tvz};
                     const float dc[4] = {cxs, cys, cxs + cys, cxs - cys};
                     const float dr[4] = {r2, r2, 1.41421357f * r2, 1.41421357f * r2};
-                    const float mg[4] = {1.0f, 1.0f, 1.41421357f, 1.41421357f};
+                    const float mg[4] = {0.0625f, 0.0625f, 0.0884f, 0.0884f};   // 1/16 px (x sqrt2 along the diagonals): the masks are per pixel now
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float c = (tau * (rx[k] * Twx + ry[k] * Twy) - rz[k] * Twz) * iq;

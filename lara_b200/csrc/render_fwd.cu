@@ -15,6 +15,7 @@ namespace srf {
 
 __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     __shared__ float4 s_rec[SRF_REC_QUADS][256];
+    __shared__ uint32_t s_mask[8][8][32];   // [warp][chunk of 32 splats][lane]: per-pixel hit words
 
     const int tid = threadIdx.x;
     const int tile = (int)a.tile_order[blockIdx.x];
@@ -60,24 +61,32 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
         // warp-uniform skip: a fully saturated warp only helps with staging
         if (__all_sync(0xffffffffu, done)) continue;
         const int nchunks = (cnt + 31) >> 5;
+
+        // ---- phase A: per-pixel hit masks.  Lane l takes splat c*32+l and rasterises its conservative
+        // alpha >= 1/255 octagon over the warp's 8x4 pixel block into a 32-bit mask (bit = lane that owns
+        // the pixel); a 32x32 bit transpose over the warp then hands every lane the word "which of these
+        // 32 splats can touch MY pixel".  A splat outside a pixel's word cannot reach alpha >= 1/255
+        // there, so skipping it changes no result.
         for (int c = 0; c < nchunks; ++c) {
-          // 32 splats per step: lane l tests splat c*32+l against the warp's pixel block; the
-          // surviving splats are then visited in list order.  Skipped splats cannot reach
-          // alpha >= 1/255 anywhere in the block, so no pixel's result changes.
-          unsigned hits;
-          {
             const int jt = (c << 5) + lane;
-            bool hit = false;
-            if (jt < cnt) {
-                hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
-            }
-            hits = __ballot_sync(0xffffffffu, hit);
-          }
-          if (__all_sync(0xffffffffu, done)) break;
-          while (hits) {
-            const int j = (c << 5) + __ffs(hits) - 1;
-            hits &= hits - 1;
-            if (done) continue;
+            uint32_t m = 0;
+            if (jt < cnt) m = octagon_pixel_mask(s_rec[2][jt], s_rec[5][jt], wrect);
+            s_mask[wid][c][lane] = transpose32(m, lane);
+        }
+        __syncwarp();
+
+        // ---- phase B: every lane walks its own hits in list order.  The warp iterates max-over-lanes
+        // times instead of once per splat that touches the block anywhere (lane utilisation there was ~30 %).
+        int c = 0;
+        uint32_t w = s_mask[wid][0][lane];
+        if (done) { w = 0; c = nchunks; }
+        for (;;) {
+            while (w == 0 && c < nchunks - 1) { ++c; w = s_mask[wid][c][lane]; }
+            const bool active = (w != 0);
+            if (!__any_sync(0xffffffffu, active)) break;
+            if (!active) continue;
+            const int j = (c << 5) + __ffs(w) - 1;
+            w &= w - 1;
             contributor = (uint32_t)(b * 256 + j + 1);
             PairEval e;
             eval_pair(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
@@ -86,6 +95,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             const float test_T = fmul_(T, fadd_(1.0f, -alpha));
             if (!(test_T >= 0.0001f)) {
                 done = true;
+                w = 0; c = nchunks;
                 continue;
             }
             const float4 q3 = s_rec[3][j];
@@ -111,7 +121,6 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             d12 = fma2(T2, mul2(pk2(m, mm), a2), d12);
             T = test_T;
             last_contributor = contributor;
-          }
         }
     }
 

@@ -169,3 +169,50 @@ __device__ __forceinline__ bool octagon_hits(const float4 q2, const float4 q5, c
                      (cu + eu.x > w.umax) || (cu + eu.y < w.umin) || (cv + ev.x > w.vmax) || (cv + ev.y < w.vmin);
     return !out;
 }
+
+// Which pixels of the warp's 8x4 block (bit = lane owning the pixel, tile_pixel()) can the splat's
+// conservative octagon touch?  Same eight half-planes as octagon_hits(), evaluated per pixel row:
+// columns [lo, hi] of row r are inside.  SRF_MASK_EPS widens every bound: the octagon is already
+// rounded outwards, this only guards the few float roundings of the row arithmetic.
+#define SRF_MASK_EPS 0.0009765625f
+__device__ __forceinline__ uint32_t octagon_pixel_mask(const float4 q2, const float4 q5, const WarpRect& w) {
+    const float cx = q2.y, cy = q2.z;
+    const unsigned ux = __float_as_uint(q5.x), uy = __float_as_uint(q5.y), uu = __float_as_uint(q5.z), uv = __float_as_uint(q5.w);
+    const float2 ex = __half22float2(*reinterpret_cast<const __half2*>(&ux));
+    const float2 ey = __half22float2(*reinterpret_cast<const __half2*>(&uy));
+    const float2 eu = __half22float2(*reinterpret_cast<const __half2*>(&uu));
+    const float2 ev = __half22float2(*reinterpret_cast<const __half2*>(&uv));
+    const float cu = cx + cy, cv = cx - cy;
+    // bounds relative to the block's first pixel centre (w.xmin, w.ymin), widened by eps
+    const float xlo = (cx + ex.x) - w.xmin - SRF_MASK_EPS, xhi = (cx + ex.y) - w.xmin + SRF_MASK_EPS;
+    const float ylo = (cy + ey.x) - w.ymin - SRF_MASK_EPS, yhi = (cy + ey.y) - w.ymin + SRF_MASK_EPS;
+    // x + y in [ulo, uhi], x - y in [vlo, vhi]  (x, y now block-relative: u0 = xmin + ymin, v0 = xmin - ymin)
+    const float ulo = (cu + eu.x) - w.umin - SRF_MASK_EPS, uhi = (cu + eu.y) - w.umin + SRF_MASK_EPS;
+    const float v0 = w.xmin - w.ymin;
+    const float vlo = (cv + ev.x) - v0 - SRF_MASK_EPS, vhi = (cv + ev.y) - v0 + SRF_MASK_EPS;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float y = (float)r;
+        const float lo = fmaxf(xlo, fmaxf(ulo - y, vlo + y));
+        const float hi = fminf(xhi, fminf(uhi - y, vhi + y));
+        int ilo = __float2int_ru(lo), ihi = __float2int_rd(hi);
+        ilo = max(ilo, 0); ihi = min(ihi, 7);
+        const bool ok = (ilo <= ihi) && (y >= ylo) && (y <= yhi);
+        const uint32_t row = ok ? ((2u << ihi) - (1u << ilo)) : 0u;
+        mask |= row << (8 * r);
+    }
+    return mask;
+}
+
+// 32x32 bit-matrix transpose across a warp: lane i passes row i, receives column i.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+    const unsigned full = 0xffffffffu;
+    uint32_t y;
+    y = __shfl_xor_sync(full, x, 16); x = (lane & 16) ? ((x & 0xffff0000u) | (y >> 16)) : ((x & 0x0000ffffu) | (y << 16));
+    y = __shfl_xor_sync(full, x, 8);  x = (lane & 8) ? ((x & 0xff00ff00u) | ((y & 0xff00ff00u) >> 8)) : ((x & 0x00ff00ffu) | ((y & 0x00ff00ffu) << 8));
+    y = __shfl_xor_sync(full, x, 4);  x = (lane & 4) ? ((x & 0xf0f0f0f0u) | ((y & 0xf0f0f0f0u) >> 4)) : ((x & 0x0f0f0f0fu) | ((y & 0x0f0f0f0fu) << 4));
+    y = __shfl_xor_sync(full, x, 2);  x = (lane & 2) ? ((x & 0xccccccccu) | ((y & 0xccccccccu) >> 2)) : ((x & 0x33333333u) | ((y & 0x33333333u) << 2));
+    y = __shfl_xor_sync(full, x, 1);  x = (lane & 1) ? ((x & 0xaaaaaaaau) | ((y & 0xaaaaaaaau) >> 1)) : ((x & 0x55555555u) | ((y & 0x55555555u) << 1));
+    return x;
+}
