@@ -114,11 +114,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             // every channel: acc = fma(T, channel * alpha, acc) -- the reference's rounding sequence,
             // two channels per FMUL2 / FFMA2
             const f32x2 a2 = bc2(alpha), T2 = bc2(T);
-            C01 = fma2(T2, mul2(pk2(q4.x, q4.y), a2), C01);
-            C2r = fma2(T2, mul2(pk2(q4.z, err), a2), C2r);
-            N01 = fma2(T2, mul2(pk2(q3.x, q3.y), a2), N01);
-            N2D = fma2(T2, mul2(pk2(q3.z, depth), a2), N2D);
-            d12 = fma2(T2, mul2(pk2(m, mm), a2), d12);
+            fma2_acc(C01, T2, mul2(pk2(q4.x, q4.y), a2));
+            fma2_acc(C2r, T2, mul2(pk2(q4.z, err), a2));
+            fma2_acc(N01, T2, mul2(pk2(q3.x, q3.y), a2));
+            fma2_acc(N2D, T2, mul2(pk2(q3.z, depth), a2));
+            fma2_acc(d12, T2, mul2(pk2(m, mm), a2));
             T = test_T;
             last_contributor = contributor;
         }

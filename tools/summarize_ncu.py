@@ -32,7 +32,11 @@ WANT = {
 def read(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    return [_one(hdr, units, vals) for vals in rows[2:] if vals]
+
+
+def _one(hdr, units, vals):
     d = {"kernel": vals[hdr.index("Kernel Name")]}
     for i, h in enumerate(hdr):
         if h in WANT:
@@ -58,7 +62,7 @@ def read(path):
 
 def main():
     tag = sys.argv[1]
-    res = [read(p) for p in sys.argv[2:]]
+    res = [d for p in sys.argv[2:] for d in read(p)]
     os.makedirs("profiles", exist_ok=True)
     json.dump(res, open(f"profiles/ncu_summary_{tag}.json", "w"), indent=1)
     with open(f"profiles/ncu_summary_{tag}.md", "w") as f:
