@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(PreprocessBwdArgs a
         dT[0] = -g0.x; dT[3] = g0.y; dT[1] = -g0.z; dT[4] = g0.w;
         dT[2] = -g1.x; dT[5] = g1.y; dT[6] = g1.z; dT[7] = g1.w;
         dT[8] = g2.x;
-        const float dmx = g2.y, dmy = g2.z;
-        dopac = g2.w;
-        const float dnx = g3.x, dny = g3.y, dnz = g3.z;
-        dcol[0] = g3.w; dcol[1] = g4.x; dcol[2] = g4.y;
+        dopac = g2.y;
+        const float dnx = g2.z, dny = g2.w, dnz = g3.x;
+        dcol[0] = g3.y; dcol[1] = g3.z; dcol[2] = g3.w;
+        const float dmx = g4.x, dmy = g4.y;
 
         const V3 Tu = v3(q0.x, q0.z, q1.x), Tv = v3(q0.y, q0.w, q1.y), Tw = v3(q1.z, q1.w, q2.x);
 

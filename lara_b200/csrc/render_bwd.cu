@@ -4,9 +4,10 @@
 // Same tiling as the forward: one CTA per 16x16 tile, one thread per pixel, the tile's
 // list walked back-to-front in shared-memory batches of 256 splats.  The reference emits
 // 10-16 global float atomics per (pixel, splat) pair, 256 threads hammering the same
-// <=18 addresses.  Here each warp first transposes-and-reduces the 18 partial
-// derivatives of a splat across its 32 lanes with a 20-shuffle reduce-scatter
-// (9+5+3+2+1), adds the warp totals into a per-batch shared-memory accumulator
+// <=18 addresses.  Here each warp first transposes-and-reduces the 16 partial
+// derivatives every contributing pair produces across its 32 lanes with a 16-shuffle
+// reduce-scatter (8+4+2+1+1; the two extra low-pass-branch values take a small butterfly
+// on the ~6 % of visits that have them), adds the warp totals into a per-batch shared-memory accumulator
 // (bank-conflict-free, 18 consecutive words per splat) and the CTA finally issues at
 // most five 128-bit vector reductions (red.global.add.v4.f32) per splat per tile.
 // Further savings the reference does not have:
@@ -33,62 +34,34 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                  : "memory");
 }
 
-// Reduce-scatter of 18 per-lane values over the warp.  Returns in `out` the warp total of
-// value `index` (index in [0,18)) or index = -1 on lanes that end up holding padding.
-__device__ __forceinline__ void warp_reduce_scatter18(const float (&v)[18], int lane, float& out, int& index) {
+// Reduce-scatter of 16 per-lane values over the warp (16 -> 8 -> 4 -> 2 -> 1 values per lane, then the
+// two lanes of a pair are combined): every lane returns the warp total of value (lane >> 1) & 15.
+// 16 shuffles; a power of two, so there is no padding logic.
+__device__ __forceinline__ float warp_reduce_scatter16(const float (&v)[16], int lane) {
     const unsigned full = 0xffffffffu;
-    const bool u4 = (lane & 16) != 0;
-    float a[9];
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0, u1 = (lane & 2) != 0;
+    float a[8], b[4], c[2];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const float keep = u4 ? v[9 + i] : v[i];
-        const float send = u4 ? v[i] : v[9 + i];
+    for (int i = 0; i < 8; ++i) {
+        const float keep = u4 ? v[8 + i] : v[i];
+        const float send = u4 ? v[i] : v[8 + i];
         a[i] = keep + __shfl_xor_sync(full, send, 16);
     }
-    int base = u4 ? 9 : 0;
-    int size = 9;
-    const bool u3 = (lane & 8) != 0;
-    float b[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float hi = (5 + i < 9) ? a[5 + i] : 0.0f;
-        const float keep = u3 ? hi : a[i];
-        const float send = u3 ? a[i] : hi;
+    for (int i = 0; i < 4; ++i) {
+        const float keep = u3 ? a[4 + i] : a[i];
+        const float send = u3 ? a[i] : a[4 + i];
         b[i] = keep + __shfl_xor_sync(full, send, 8);
     }
-    base += u3 ? 5 : 0;
-    size = u3 ? max(size - 5, 0) : min(size, 5);
-    const bool u2 = (lane & 4) != 0;
-    float c[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float hi = (3 + i < 5) ? b[3 + i] : 0.0f;
-        const float keep = u2 ? hi : b[i];
-        const float send = u2 ? b[i] : hi;
-        c[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-    base += u2 ? 3 : 0;
-    size = u2 ? max(size - 3, 0) : min(size, 3);
-    const bool u1 = (lane & 2) != 0;
-    float d[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const float hi = (2 + i < 3) ? c[2 + i] : 0.0f;
-        const float keep = u1 ? hi : c[i];
-        const float send = u1 ? c[i] : hi;
-        d[i] = keep + __shfl_xor_sync(full, send, 2);
+        const float keep = u2 ? b[2 + i] : b[i];
+        const float send = u2 ? b[i] : b[2 + i];
+        c[i] = keep + __shfl_xor_sync(full, send, 4);
     }
-    base += u1 ? 2 : 0;
-    size = u1 ? max(size - 2, 0) : min(size, 2);
-    const bool u0 = (lane & 1) != 0;
-    {
-        const float keep = u0 ? d[1] : d[0];
-        const float send = u0 ? d[0] : d[1];
-        out = keep + __shfl_xor_sync(full, send, 1);
-    }
-    base += u0 ? 1 : 0;
-    size = u0 ? max(size - 1, 0) : min(size, 1);
-    index = size > 0 ? base : -1;
+    float d = (u1 ? c[1] : c[0]) + __shfl_xor_sync(full, u1 ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(full, d, 1);
+    return d;
 }
 
 __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
@@ -206,6 +179,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
             float g[18];
 #pragma unroll
             for (int i = 0; i < 18; ++i) g[i] = 0.0f;
+            bool lowpass = false;
 
             if (contrib) {
                 const float4 q3 = s_rec[3][j];
@@ -286,6 +260,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
                     g[SRF_G_DT + 8] = fmaf(pixx, Dz.x, fmaf(npixy, Dz.y, dL_dz));
                 } else {
                     // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
+                    lowpass = true;
                     const float2 gm = up2(mul2(pk2(e.dx, e.dy), bc2(dL_dG * (-2.0f * G))));
                     g[SRF_G_DMEAN2D + 0] = gm.x;
                     g[SRF_G_DMEAN2D + 1] = gm.y;
@@ -294,10 +269,24 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
                 g[SRF_G_DOPAC] = G * dL_dalpha;
             }
 
-            float total;
-            int index;
-            warp_reduce_scatter18(g, lane, total, index);
-            if (index >= 0) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + index], total);
+            // slots 0..15 in one power-of-two reduce-scatter; even lanes own value lane >> 1
+            {
+                float v16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v16[i] = g[i];
+                const float total = warp_reduce_scatter16(v16, lane);
+                if ((lane & 1) == 0) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + (lane >> 1)], total);
+            }
+            // the two dL/dmean2D values exist only on low-pass lanes (~6 % of the visits)
+            if (__any_sync(0xffffffffu, lowpass)) {
+                float m0 = g[SRF_G_DMEAN2D + 0], m1 = g[SRF_G_DMEAN2D + 1];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+                }
+                if (lane < 2) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + SRF_G_DMEAN2D + lane], lane ? m1 : m0);
+            }
             if (lane == 0) s_touched[j] = 1;
           }
         }
@@ -308,7 +297,9 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
             const float4* g4 = reinterpret_cast<const float4*>(s_grad + tid * SRF_GRAD_FLOATS);
             float* dst = a.ggrad + (size_t)s_id[tid] * SRF_GRAD_FLOATS;
 #pragma unroll
-            for (int k = 0; k < SRF_GRAD_FLOATS / 4; ++k) red_add_v4(dst + 4 * k, g4[k]);
+            for (int k = 0; k < 4; ++k) red_add_v4(dst + 4 * k, g4[k]);
+            const float4 gm = g4[4];                     // dL/dmean2D: only if a low-pass pair touched the splat
+            if (gm.x != 0.0f || gm.y != 0.0f) red_add_v4(dst + 16, gm);
         }
         // (the same thread re-zeroes its row and restages its slot at the top of the loop;
         //  s_rec rows are protected by the barrier above)

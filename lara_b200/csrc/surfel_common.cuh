@@ -29,11 +29,13 @@
 #define SRF_GRAD_FLOATS 20  // per-Gaussian gradient accumulation record (5 x float4)
 
 // gradient accumulation record layout (floats)
+// slots 0..15 are what every contributing pair produces (one power-of-two reduce-scatter); the two
+// low-pass-branch values follow
 #define SRF_G_DT 0        // 9: (dk.x, -dl.x, dk.y, -dl.y, dk.z, -dl.z) = (-dL/dTu, dL/dTv) interleaved, then dL/dTw
-#define SRF_G_DMEAN2D 9   // 2: dL/dmean2D (low-pass branch)
-#define SRF_G_DOPAC 11    // 1
-#define SRF_G_DNORMAL 12  // 3
-#define SRF_G_DCOLOR 15   // 3
+#define SRF_G_DOPAC 9     // 1
+#define SRF_G_DNORMAL 10  // 3
+#define SRF_G_DCOLOR 13   // 3
+#define SRF_G_DMEAN2D 16  // 2: dL/dmean2D (low-pass branch only)
 // 18,19: padding
 
 #define SRF_NEAR_F 0.2f
