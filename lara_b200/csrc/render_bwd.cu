@@ -64,24 +64,25 @@ __device__ __forceinline__ float warp_reduce_scatter16(const float (&v)[16], int
     return d;
 }
 
-__global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
-    __shared__ float4 s_rec[SRF_REC_QUADS][256];
-    __shared__ __align__(16) float s_grad[256 * SRF_GRAD_FLOATS];
-    __shared__ uint32_t s_id[256];
-    __shared__ int s_touched[256];
-    __shared__ int s_wmax[8];
+__global__ void __launch_bounds__(SRF_CTA_THREADS, 768 / SRF_CTA_THREADS) render_bwd_kernel(RenderBwdArgs a) {
+    __shared__ float4 s_rec[SRF_REC_QUADS][SRF_BATCH];
+    __shared__ __align__(16) float s_grad[SRF_BATCH * SRF_GRAD_FLOATS];
+    __shared__ uint32_t s_id[SRF_BATCH];
+    __shared__ int s_touched[SRF_BATCH];
+    __shared__ int s_wmax[SRF_CTA_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int tile = (int)a.tile_order[blockIdx.x];
+    const int tile = (int)a.tile_order[blockIdx.x / SRF_CTAS_PER_TILE];
+    const int gw = (int)(blockIdx.x % SRF_CTAS_PER_TILE) * SRF_CTA_WARPS + wid;   // which of the tile's eight 8x4 blocks
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
-    tile_pixel(tid, lx, ly);
+    tile_pixel(gw * 32 + lane, lx, ly);
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     const size_t npix = (size_t)a.W * a.H;
     const size_t pix = (size_t)pyi * a.W + pxi;
-    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
+    const WarpRect wrect = make_warp_rect(txi, tyi, gw);
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
     __syncthreads();
     int n_eff = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) n_eff = max(n_eff, s_wmax[w]);
-    const int rounds = (n_eff + 255) >> 8;
+    for (int w = 0; w < SRF_CTA_WARPS; ++w) n_eff = max(n_eff, s_wmax[w]);
+    const int rounds = (n_eff + SRF_BATCH - 1) / SRF_BATCH;
 
     // accum_rec / last_* recursions of backward.cu:331-385, two channels per packed fp32x2 register:
     // (c0,c1) (c2,depth) (n0,n1) (n2,alpha); the matching upstream gradients are paired the same way
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
 
     for (int b = 0; b < rounds; ++b) {
         // stage batch b (back to front) and clear the accumulator rows this thread owns
-        const int pos_mine = n_eff - 1 - (b * 256 + tid);
+        const int pos_mine = n_eff - 1 - (b * SRF_BATCH + tid);
         if (pos_mine >= 0) {
             const uint32_t id = __ldg(a.point_list + range.x + pos_mine);
             s_id[tid] = id;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
         }
         __syncthreads();
 
-        const int cnt = min(256, n_eff - b * 256);
+        const int cnt = min(SRF_BATCH, n_eff - b * SRF_BATCH);
         const int nchunks = (cnt + 31) >> 5;
         for (int c = 0; c < nchunks; ++c) {
           // warp-level cull, 32 splats per ballot: skip splats behind the warp's deepest
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
           {
             const int jt = (c << 5) + lane;
             bool hit = false;
-            if (jt < cnt && n_eff - 1 - (b * 256 + jt) < wmax) {
+            if (jt < cnt && n_eff - 1 - (b * SRF_BATCH + jt) < wmax) {
                 hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
             }
             hits = __ballot_sync(0xffffffffu, hit);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderBwdArgs a) {
           while (hits) {
             const int j = (c << 5) + __ffs(hits) - 1;
             hits &= hits - 1;
-            const int pos = n_eff - 1 - (b * 256 + j);   // 0-based position in the tile list
+            const int pos = n_eff - 1 - (b * SRF_BATCH + j);   // 0-based position in the tile list
             bool contrib = inside && pos < last_contributor;
             PairEval e;
             const float4 q0 = s_rec[0][j], q1 = s_rec[1][j], q2 = s_rec[2][j];
@@ -310,7 +311,7 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
     if (ntiles <= 0) return cudaSuccess;
     prof_start(K_RENDER_BWD, stream);
-    render_bwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    render_bwd_kernel<<<ntiles * SRF_CTAS_PER_TILE, SRF_CTA_THREADS, 0, stream>>>(a);
     prof_stop(K_RENDER_BWD, stream);
     return cudaGetLastError();
 }

@@ -13,26 +13,27 @@
 
 namespace srf {
 
-__global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
-    __shared__ float4 s_rec[SRF_REC_QUADS][256];
-    __shared__ uint32_t s_mask[8][8][32];   // [warp][chunk of 32 splats][lane]: per-pixel hit words
+__global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) render_fwd_kernel(RenderFwdArgs a) {
+    __shared__ float4 s_rec[SRF_REC_QUADS][SRF_BATCH];
+    __shared__ uint32_t s_mask[SRF_CTA_WARPS][SRF_BATCH_CHUNKS][32];   // [warp][chunk of 32 splats][lane]: per-pixel hit words
 
     const int tid = threadIdx.x;
-    const int tile = (int)a.tile_order[blockIdx.x];
+    const int tile = (int)a.tile_order[blockIdx.x / SRF_CTAS_PER_TILE];
+    const int gw = (int)(blockIdx.x % SRF_CTAS_PER_TILE) * SRF_CTA_WARPS + (tid >> 5);   // which of the tile's eight 8x4 blocks
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
-    tile_pixel(tid, lx, ly);
+    tile_pixel(gw * 32 + (tid & 31), lx, ly);
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     // pixel-centre rectangle of this warp's 8x4 block, for the warp-level cull
     const int lane = tid & 31, wid = tid >> 5;
-    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
+    const WarpRect wrect = make_warp_rect(txi, tyi, gw);
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;  // overflowed optimistic capacity: host re-runs
     const int n = (int)(range.y - range.x);
-    const int rounds = (n + 255) >> 8;
+    const int rounds = (n + SRF_BATCH - 1) / SRF_BATCH;
 
     bool done = !inside;
     float T = 1.0f;
@@ -46,10 +47,10 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
     uint32_t median_contributor = 0;
 
     int todo = n;
-    for (int b = 0; b < rounds; ++b, todo -= 256) {
+    for (int b = 0; b < rounds; ++b, todo -= SRF_BATCH) {
         // whole tile saturated -> stop (reference forward.cu:334-336)
-        if (__syncthreads_count(done) == 256) break;
-        const int progress = b * 256 + tid;
+        if (__syncthreads_count(done) == SRF_CTA_THREADS) break;
+        const int progress = b * SRF_BATCH + tid;
         if (progress < n) {
             const uint32_t id = __ldg(a.point_list + range.x + progress);
             const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][tid] = ldg4(r + k);
         }
         __syncthreads();
-        const int cnt = min(256, todo);
+        const int cnt = min(SRF_BATCH, todo);
         // warp-uniform skip: a fully saturated warp only helps with staging
         if (__all_sync(0xffffffffu, done)) continue;
         const int nchunks = (cnt + 31) >> 5;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderFwdArgs a) {
             if (!active) continue;
             const int j = (c << 5) + __ffs(w) - 1;
             w &= w - 1;
-            contributor = (uint32_t)(b * 256 + j + 1);
+            contributor = (uint32_t)(b * SRF_BATCH + j + 1);
             PairEval e;
             eval_pair(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
             if (!e.valid) continue;
@@ -153,7 +154,7 @@ cudaError_t launch_render_fwd(const RenderFwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
     if (ntiles <= 0) return cudaSuccess;
     prof_start(K_RENDER_FWD, stream);
-    render_fwd_kernel<<<ntiles, 256, 0, stream>>>(a);
+    render_fwd_kernel<<<ntiles * SRF_CTAS_PER_TILE, SRF_CTA_THREADS, 0, stream>>>(a);
     prof_stop(K_RENDER_FWD, stream);
     return cudaGetLastError();
 }

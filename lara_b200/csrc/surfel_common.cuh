@@ -40,6 +40,15 @@
 
 #define SRF_NEAR_F 0.2f
 
+// Blend CTAs: a 16x16 tile is eight 8x4 warp blocks; one CTA owns SRF_CTA_WARPS of them (a 16x8 half
+// tile) and walks the tile's list in rounds of SRF_BATCH staged splats (one per thread).  Smaller CTAs
+// wait less at the per-round barriers (the warps of a tile are unevenly loaded).
+#define SRF_CTA_WARPS 8
+#define SRF_CTA_THREADS (SRF_CTA_WARPS * 32)
+#define SRF_BATCH SRF_CTA_THREADS
+#define SRF_BATCH_CHUNKS (SRF_BATCH / 32)
+#define SRF_CTAS_PER_TILE (8 / SRF_CTA_WARPS)
+
 // Per-tile counters live in their own 256-byte block (word 0: instance count, word 1:
 // bucket cursor).  Dense u32 counters put every atomic of a view into a handful of cache
 // lines -- i.e. a handful of L2 slices -- and serialise there; one block per tile spreads
