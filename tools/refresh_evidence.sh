@@ -1,4 +1,4 @@
-# round-1 final evidence refresh (run on the GPU box):  bash tools/_final.sh
+# round-1 final evidence refresh (run on the GPU box):  bash tools/refresh_evidence.sh
 mkdir -p gpurun_out
 python bench.py --impl reference --steps 20 --warmup 5 2>gpurun_out/bench_ref_r01b.err | tail -1 > gpurun_out/bench_ref_r01b.json
 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r01b.err | tail -1 > gpurun_out/bench_r01b.json
