@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "rasterizer fwd+bwd views/sec at 131072 Gaussians x 512x512"
+METRIC = "rasterizer fwd+bwd views/sec at {P} Gaussians x {S}x{S}"      # formatted with --P / --size (defaults: the north-star point)
 UNIT = "views/s"
 KERNELS_PER_VIEW = 8  # preprocess_fwd, tile_scan, scatter, sort_small, sort_big, render_fwd, render_bwd, preprocess_bwd
 
@@ -184,7 +184,7 @@ def run_reference(args, rank, local, world):
     from lara_b200 import scene as S
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    base = {"impl": "reference", "metric": METRIC.format(P=args.P, S=args.size), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic"}
     if not REF.available():
@@ -368,7 +368,8 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get("render_bwd_dram_bytes_per_launch")
+                if args.P == 131072 and args.size == 512:      # the capture is of the default workload only
+                    traffic = json.load(f).get("render_bwd_dram_bytes_per_launch")
         except Exception:
             pass
         achieved = alg_bytes / dur_s / 1e9
@@ -380,7 +381,7 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC.format(P=args.P, S=args.size), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"scene({args.P},seed0) {args.size}x{args.size} sh1 white bg, {V} views/GPU/step fwd+bwd, "
