@@ -140,3 +140,28 @@ def test_grad_buffer_layout():
     assert float(g.flat.sum()) == 20.0
     g.zero_()
     assert float(g.flat.abs().sum()) == 0.0
+
+
+def test_concat_views_matches_the_callers_cat():
+    """multiview.concat_views == what lightning/network.py:525 builds from per-view frames
+    (`torch.cat([frame[k] for frame in views], dim=1)`)."""
+    import torch
+    from lara_b200.multiview import concat_views
+    V, H, W = 3, 4, 5
+    g = torch.Generator().manual_seed(0)
+    stacked = {"image": torch.rand((V, H, W, 3), generator=g), "acc_map": torch.rand((V, H, W), generator=g),
+               "radii": torch.zeros((V, 7), dtype=torch.int32)}
+    out = concat_views(stacked)
+    assert sorted(out) == ["acc_map", "image"]              # radii is per Gaussian, not an image
+    frames = [{k: stacked[k][v] for k in ("image", "acc_map")} for v in range(V)]
+    for k in ("image", "acc_map"):
+        assert torch.equal(out[k], torch.cat([f[k] for f in frames], dim=1))
+
+
+def test_render_scene_views_rejects_empty_view_list():
+    import pytest
+    import torch
+    from lara_b200.multiview import render_scene_views
+    z = torch.zeros((0, 3))
+    with pytest.raises(ValueError):
+        render_scene_views(z, z, z, z, z, [])
