@@ -2,7 +2,7 @@
 // Replaces reference backward.cu:143-449 (renderCUDA backward).
 //
 // Same tiling as the forward: one CTA per 16x16 tile, one thread per pixel, the tile's
-// list walked back-to-front in shared-memory batches of 256 splats.  The reference emits
+// list walked back-to-front in shared-memory rounds of SRF_BATCH = 256 splats.  The reference emits
 // 10-16 global float atomics per (pixel, splat) pair, 256 threads hammering the same
 // <=18 addresses.  Here each warp first transposes-and-reduces the 16 partial
 // derivatives every contributing pair produces across its 32 lanes with a 16-shuffle

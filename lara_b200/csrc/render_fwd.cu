@@ -1,13 +1,15 @@
 // render_fwd.cu -- per-tile front-to-back alpha compositing (K6).
 // Replaces reference forward.cu:265-463 (renderCUDA forward).
 //
-// One 256-thread CTA per 16x16 tile, one thread per pixel (each warp owns an 8x4 pixel
-// block).  The tile's depth-sorted Gaussian list is consumed in batches of 256: every
-// thread gathers one 96 B GeomRecord with six 128-bit loads and stages it in shared
-// memory as six float4 planes, so the inner loop reads each splat with broadcast
-// LDS.128 (no bank conflicts) and never touches global memory -- including the colour,
-// which the reference fetches from global memory per contributing pixel.
-// Arithmetic and predicates follow the reference exactly (see eval_pair()).
+// One CTA (SRF_CTA_WARPS = 8 warps) per 16x16 tile, one thread per pixel (each warp owns an
+// 8x4 pixel block).  The tile's depth-sorted Gaussian list is consumed in rounds of SRF_BATCH
+// = 256: every thread gathers one 96 B GeomRecord with six 128-bit loads and stages it in
+// shared memory as six float4 planes, so the inner loop never touches global memory --
+// including the colour, which the reference fetches from global memory per contributing pixel.
+// Per round each warp builds per-pixel hit masks (the splat's conservative alpha >= 1/255
+// octagon rasterised over the warp's block, transposed across the warp) and every lane then
+// walks its own hits in list order, reading the records at per-lane indices (phases A / B
+// below).  Arithmetic and predicates follow the reference exactly (see eval_pair()).
 #include "surfel_common.cuh"
 #include "surfel_kernels.h"
 

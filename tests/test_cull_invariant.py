@@ -1,0 +1,115 @@
+"""CPU check of the invariant the blend kernels' cull rests on:
+
+    a (pixel, splat) pair outside the splat's conservative screen octagon can never reach
+    alpha >= 1/255, so skipping it changes no result.
+
+The octagon is restated here in numpy exactly as lara_b200/csrc/preprocess.cu computes it (the
+tau-ellipse's extent along x, y, x+y, x-y from the reference's AABB quadratic form with
+diag(tau,tau,-1), the rho2d disc, the 1/16 px + 0.1 % margin, outward fp16 rounding) and the pair
+evaluation as reference forward.cu:353-398 does it; the homographies / centres come from the CPU
+oracle.  Brute force over every (pixel, splat) pair of small scenes, needle-like splats included.
+The CUDA implementation of the same test is covered by the bit-exact GPU parity tests."""
+import numpy as np
+import pytest
+import torch
+
+from lara_b200 import scene as S
+from oracle import oracle as O
+
+f32 = np.float32
+
+
+def _half_outward(lo, hi):
+    """fp16 rounding towards -inf for lo, +inf for hi (cvt.rd / cvt.ru)."""
+    with np.errstate(over="ignore", invalid="ignore"):
+        l16 = lo.astype(np.float16); h16 = hi.astype(np.float16)
+        l16 = np.where(l16.astype(f32) > lo, np.nextafter(l16, np.float16(-np.inf)), l16)
+        h16 = np.where(h16.astype(f32) < hi, np.nextafter(h16, np.float16(np.inf)), h16)
+    return l16.astype(f32), h16.astype(f32)
+
+
+def _octagon(T, centre, opac):
+    """[P,4] lo / hi offsets from the centre along x, y, x+y, x-y (preprocess.cu, the cull block)."""
+    Tu, Tv, Tw = T[:, 0:3], T[:, 3:6], T[:, 6:9]
+    P = T.shape[0]
+    lo = np.full((P, 4), 3.0e38, f32); hi = np.full((P, 4), -3.0e38, f32)
+    vis = opac >= f32(0.00392156862745098)
+    with np.errstate(all="ignore"):
+        tau = f32(2.0) * np.log(opac * f32(255.0)) * f32(1.0001) + f32(1.0e-3)
+        r2 = np.sqrt(f32(0.5) * tau)
+        qw = tau * (Tw[:, 0] ** 2 + Tw[:, 1] ** 2) - Tw[:, 2] ** 2
+        iq = f32(1.0) / qw
+        rows = [Tu, Tv, Tu + Tv, Tu - Tv]
+        dc = [centre[:, 0], centre[:, 1], centre[:, 0] + centre[:, 1], centre[:, 0] - centre[:, 1]]
+        dr = [r2, r2, f32(1.41421357) * r2, f32(1.41421357) * r2]
+        mg = [f32(0.0625), f32(0.0625), f32(0.0884), f32(0.0884)]
+        for k in range(4):
+            r = rows[k]
+            c = (tau * (r[:, 0] * Tw[:, 0] + r[:, 1] * Tw[:, 1]) - r[:, 2] * Tw[:, 2]) * iq
+            h = np.sqrt(np.maximum(f32(0.0), c * c - (tau * (r[:, 0] ** 2 + r[:, 1] ** 2) - r[:, 2] ** 2) * iq))
+            l0 = np.minimum(dc[k] - dr[k], c - h); h0 = np.maximum(dc[k] + dr[k], c + h)
+            m = mg[k] + f32(1.0e-3) * (h0 - l0)
+            bounded = vis & (qw < 0)
+            lo[:, k] = np.where(bounded, l0 - m - dc[k], np.where(vis, f32(-3.0e38), f32(3.0e38)))
+            hi[:, k] = np.where(bounded, h0 + m - dc[k], np.where(vis, f32(3.0e38), f32(-3.0e38)))
+    return _half_outward(lo, hi)
+
+
+def _valid_pairs(T, centre, opac, H, W):
+    """[P,H,W] bool: the pair is blended by the reference (forward.cu:353-398 predicates)."""
+    ys, xs = np.meshgrid(np.arange(H, dtype=f32) + f32(0.5), np.arange(W, dtype=f32) + f32(0.5), indexing="ij")
+    px, py = xs[None], ys[None]
+    g = lambda i: T[:, i][:, None, None]
+    with np.errstate(all="ignore"):
+        kx, ky, kz = px * g(6) - g(0), px * g(7) - g(1), px * g(8) - g(2)
+        lx, ly, lz = py * g(6) - g(3), py * g(7) - g(4), py * g(8) - g(5)
+        pz = kx * ly - ky * lx
+        sx = (ky * lz - kz * ly) / pz
+        sy = (kz * lx - kx * lz) / pz
+        rho3d = sx * sx + sy * sy
+        dx, dy = centre[:, 0][:, None, None] - px, centre[:, 1][:, None, None] - py
+        rho2d = f32(2.0) * (dx * dx + dy * dy)
+        rho = np.minimum(rho3d, rho2d)
+        depth = np.where(rho3d <= rho2d, sx * g(6) + sy * g(7) + g(8), g(8))
+        alpha = np.minimum(f32(0.99), opac[:, None, None] * np.exp(f32(-0.5) * rho))
+        # NaN rho (p.z == 0) makes every comparison false -> not valid, as in the kernels
+        return (pz != 0) & ~(depth < f32(0.2)) & (rho >= 0) & (alpha >= f32(0.00392156862745098)), px, py
+
+
+@pytest.mark.parametrize("seed,needles,scale", [(0, False, 1.0), (1, True, 1.0), (2, False, 3.0), (3, True, 0.4)])
+def test_no_blended_pair_lies_outside_its_octagon(seed, needles, scale):
+    H = W = 64
+    P = 1500
+    sc = S.scene(P, seed)
+    sc["scales"] = sc["scales"] * 6.0 * scale                     # P is small: LaRa-like footprints in pixels
+    if needles:
+        sc["scales"][:, 1] *= 0.04                                # edge-on / needle-like conics
+    cam = S.cameras(3, H, W, seed)[seed % 3]
+    O.load()
+    run = O.run_scene(sc, cam, torch.ones(3))
+    vis = np.asarray(run.radii) > 0
+    assert vis.sum() > P // 2
+    T = np.asarray(run.transMat)[vis].astype(f32)
+    centre = np.asarray(run.center)[vis].astype(f32)
+    opac = sc["opacities"].numpy().reshape(-1)[vis].astype(f32)
+
+    lo, hi = _octagon(T, centre, opac)
+    valid, px, py = _valid_pairs(T, centre, opac, H, W)
+    eps = f32(0.0009765625)                                       # SRF_MASK_EPS of octagon_pixel_mask()
+    c = lambda a: a[:, None, None]
+    coords = [px - c(centre[:, 0]), py - c(centre[:, 1]),
+              (px + py) - c(centre[:, 0] + centre[:, 1]), (px - py) - c(centre[:, 0] - centre[:, 1])]
+    inside = np.ones_like(valid)
+    for k in range(4):
+        inside &= (coords[k] >= c(lo[:, k]) - eps) & (coords[k] <= c(hi[:, k]) + eps)
+    missed = valid & ~inside
+    assert int(missed.sum()) == 0, f"{int(missed.sum())} blended pairs outside the cull octagon"
+    # negative control: an octagon 1 px too small does lose blended pairs (the check has teeth)
+    shrunk = np.ones_like(valid)
+    for k in range(4):
+        shrunk &= (coords[k] >= c(lo[:, k]) + f32(1.0)) & (coords[k] <= c(hi[:, k]) - f32(1.0))
+    assert int((valid & ~shrunk).sum()) > 0
+    # ... and the octagon is not vacuous: a fair share of what it keeps is really blended
+    assert valid.sum() > 1000
+    # (thin oblique ellipses are where an octagon is loosest: ~0.25 for the needle scenes, ~0.6 otherwise)
+    assert valid.sum() / max(int(inside.sum()), 1) > (0.15 if needles else 0.35)
