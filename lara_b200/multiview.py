@@ -103,9 +103,7 @@ class _RenderSceneViews(torch.autograd.Function):
         centers, shs, scales, rot, rays, *saved = ctx.saved_tensors
         dev = centers.device
         settings_list = ctx.settings_list
-        V = len(settings_list)
         P, M = int(centers.shape[0]), int(shs.shape[1])
-        H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
 
         def c(t):
             return None if t is None else t.contiguous()

@@ -17,7 +17,6 @@ corresponding input was given (autograd discards them otherwise).
 """
 from __future__ import annotations
 
-import ctypes
 import os
 from typing import NamedTuple, Optional
 
