@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SRF_ABI_VERSION 2
+#define SRF_ABI_VERSION 3
 
 /* cudaStream_t without pulling in cuda_runtime.h */
 typedef void* srf_stream_t;
@@ -148,6 +148,79 @@ int srf_epilogue_backward(srf_stream_t stream, int image_height, int image_width
                           const float* g_image, const float* g_depth, const float* g_acc_map,
                           const float* g_rend_normal, const float* g_depth_normal, const float* g_rend_dist,
                           float* scratch, float* dL_dcolor, float* dL_dallmap);
+
+/* ---- all target views of one scene in one launch set (next-row: the caller loop -----------------
+ * lightning/network.py:484-497 renders the 8-16 target views of ONE Gaussian set one call at a
+ * time; no reference native counterpart).  Same three stages as above, but every kernel carries a
+ * view dimension, so a scene costs one launch set instead of V.
+ *
+ *   cams          : device array of V camera records, SRF_CAM_FLOATS floats each:
+ *                   [0..15] viewmatrix (as `viewmatrix` above), [16..18] campos, [19..21] background
+ *                   colour, [22..23] padding.  All views share tan_fovx/tan_fovy and the image size.
+ *   workspaces    : V per-view workspaces of identical layout back to back; total sizes from
+ *                   srf_views_workspace_bytes: bytes[0..5] = geom, tile, image, entries, point_list,
+ *                   backward scratch.  `capacity` is the per-view instance capacity.
+ *   radii         : [V,P];  out_color [V,3,H,W];  out_others [V,8,H,W];  upstream gradients alike.
+ *   num_rendered_host : pinned host array of V uint32 (may be NULL).
+ *   srf_views_backward: the per-Gaussian backward sums the gradients of all V views in registers
+ *                   and writes (or, accumulate != 0, adds) every output row once.  dL_dmeans2D (may be
+ *                   NULL) receives the sum over views of the densification statistic.             */
+#define SRF_CAM_FLOATS 24
+#define SRF_CAM_VIEW 0
+#define SRF_CAM_CAMPOS 16
+#define SRF_CAM_BG 19
+int srf_views_workspace_bytes(int V, int P, int H, int W, size_t capacity, size_t bytes[6]);
+int srf_views_forward_preprocess(srf_stream_t stream, int V, int P, int D, int M,
+                                 const float* means3D, const float* shs, const float* colors_precomp,
+                                 const float* opacities, const float* scales, const float* rotations,
+                                 const float* transMat_precomp, const float* cams,
+                                 float tan_fovx, float tan_fovy, int image_height, int image_width,
+                                 int prefiltered, int* radii, void* geom_state, void* tile_state,
+                                 uint32_t* num_rendered_host, int raw_activations);
+int srf_views_forward_render(srf_stream_t stream, int V, int P, int image_height, int image_width,
+                             size_t capacity, const void* geom_state, void* tile_state,
+                             void* entries, uint32_t* point_list, void* image_state,
+                             const float* cams, float* out_color, float* out_others);
+int srf_views_backward(srf_stream_t stream, int V, int P, int D, int M, int image_height, int image_width,
+                       size_t capacity, const float* cams,
+                       const float* means3D, const float* shs, int colors_were_precomputed,
+                       const float* scales, const float* rotations, int transmat_was_precomputed,
+                       float tan_fovx, float tan_fovy, const int* radii,
+                       const void* geom_state, const void* tile_state, const uint32_t* point_list,
+                       const void* image_state,
+                       const float* dL_dout_color, const float* dL_dout_others,
+                       void* scratch, int accumulate,
+                       float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                       float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dtransMat,
+                       int raw_activations);
+/* the fused render_img epilogue over V stacked views ([V,C,H,W] images, rays [V,H,W,6], `cams` as above) */
+int srf_views_epilogue_forward(srf_stream_t stream, int V, int image_height, int image_width, float depth_ratio,
+                               const float* color, const float* allmap, const float* rays, const float* cams,
+                               float* image, float* depth, float* acc_map, float* rend_normal, float* depth_normal,
+                               float* rend_dist);
+int srf_views_epilogue_backward(srf_stream_t stream, int V, int image_height, int image_width, float depth_ratio,
+                                const float* color, const float* allmap, const float* rays, const float* cams,
+                                const float* g_image, const float* g_depth, const float* g_acc_map,
+                                const float* g_rend_normal, const float* g_depth_normal, const float* g_rend_dist,
+                                float* scratch, float* dL_dcolor, float* dL_dallmap);
+
+/* ---- fused loss -> dL/d(render_img outputs) producer (next-row: lightning/loss.py:33-60) ------------
+ * The rasterizer-facing terms of LaRa's loss over the V stacked views of a scene:
+ *   sums[0] = sum (image - target)^2,  sums[1] = sum rend_dist,  sums[2] = sum (1 - <rend_normal, depth_normal>) acc_map
+ * (with_reg == 0: only sums[0]; the caller divides by the element counts of the reference's mean()s and applies the
+ * weights 1, 1000, 0.2; MS-SSIM stays a library call).  Images planar stacked [V,C,H,W] as the fused epilogue writes
+ * them; `target_hwc` is the batch's own channel-last [V,H,W,3].  srf_loss_backward writes the four gradient maps
+ * srf_views_epilogue_backward consumes, scaled by the device scalar `upstream` (NULL = 1):
+ *   g_image = 2 w_mse (image - target), g_rend_dist = w_dist, g_rend_normal = -w_normal acc depth_normal,
+ *   g_depth_normal = -w_normal acc rend_normal   (w_* = weight / element count).                          */
+int srf_loss_forward(srf_stream_t stream, int V, int image_height, int image_width, int with_reg,
+                     const float* image, const float* target_hwc, const float* rend_normal, const float* depth_normal,
+                     const float* acc_map, const float* rend_dist, double* sums);
+int srf_loss_backward(srf_stream_t stream, int V, int image_height, int image_width, int with_reg,
+                      float w_mse, float w_dist, float w_normal,
+                      const float* image, const float* target_hwc, const float* rend_normal, const float* depth_normal,
+                      const float* acc_map, const float* upstream,
+                      float* g_image, float* g_rend_normal, float* g_depth_normal, float* g_rend_dist);
 
 /* ---- optional per-kernel timing (no reference counterpart; used by bench.py's roofline) --
  * Between srf_profile_begin() and srf_profile_end() every kernel launch made by this

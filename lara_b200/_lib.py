@@ -13,7 +13,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsurfel_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
+CAM_FLOATS, CAM_VIEW, CAM_CAMPOS, CAM_BG = 24, 0, 16, 19      # include/surfel_rasterizer.h SRF_CAM_*
 
 # name -> (restype, argtypes); mirrors include/surfel_rasterizer.h one to one
 _P = c_void_p
@@ -58,6 +59,41 @@ SIGNATURES = {
         _P, _P, _P, _P,                          # dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat
         c_int,                                   # raw_activations
     ]),
+    "srf_views_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_size_t, POINTER(c_size_t)]),
+    "srf_views_forward_preprocess": (c_int, [
+        _P, c_int, c_int, c_int, c_int,     # stream, V, P, D, M
+        _P, _P, _P,                         # means3D, shs, colors_precomp
+        _P, _P, _P,                         # opacities, scales, rotations
+        _P, _P,                             # transMat_precomp, cams
+        c_float, c_float, c_int, c_int,     # tan_fovx, tan_fovy, H, W
+        c_int,                              # prefiltered
+        _P, _P, _P,                         # radii, geom_state, tile_state
+        _P,                                 # num_rendered_host
+        c_int,                              # raw_activations
+    ]),
+    "srf_views_forward_render": (c_int, [
+        _P, c_int, c_int, c_int, c_int,     # stream, V, P, H, W
+        c_size_t, _P, _P,                   # capacity, geom_state, tile_state
+        _P, _P, _P,                         # entries, point_list, image_state
+        _P, _P, _P,                         # cams, out_color, out_others
+    ]),
+    "srf_views_backward": (c_int, [
+        _P, c_int, c_int, c_int, c_int, c_int, c_int,   # stream, V, P, D, M, H, W
+        c_size_t, _P,                            # capacity, cams
+        _P, _P, c_int,                           # means3D, shs, colors_were_precomputed
+        _P, _P, c_int,                           # scales, rotations, transmat_was_precomputed
+        c_float, c_float, _P,                    # tan_fovx, tan_fovy, radii
+        _P, _P, _P, _P,                          # geom_state, tile_state, point_list, image_state
+        _P, _P,                                  # dL_dout_color, dL_dout_others
+        _P, c_int,                               # scratch, accumulate
+        _P, _P, _P, _P,                          # dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors
+        _P, _P, _P, _P,                          # dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat
+        c_int,                                   # raw_activations
+    ]),
+    "srf_views_epilogue_forward": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srf_views_epilogue_backward": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srf_loss_forward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "srf_loss_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srf_mark_visible": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "srf_epilogue_forward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srf_epilogue_backward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -117,6 +153,13 @@ def binning_sizes(lib, capacity: int):
     e, p = c_size_t(), c_size_t()
     check(lib.srf_binning_bytes(capacity, ctypes.byref(e), ctypes.byref(p)), lib)
     return e.value, p.value
+
+
+def views_sizes(lib, V: int, P: int, H: int, W: int, capacity: int):
+    """(geom, tile, image, entries, point_list, backward scratch) bytes for V back-to-back per-view workspaces."""
+    b = (c_size_t * 6)()
+    check(lib.srf_views_workspace_bytes(V, P, H, W, capacity, b), lib)
+    return tuple(int(x) for x in b)
 
 
 def layout(lib, P: int, H: int, W: int):

@@ -60,6 +60,18 @@ constexpr int kSortSmallThreads = 256;
 
 __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     __shared__ uint32_t s_warp[32];
+    {   // view of this CTA: own geom / tile workspace and binning buffers
+        const int view = blockIdx.y;
+        a.depths = view_ptr(a.depths, view, a.geom_stride);
+        a.rects = view_ptr(a.rects, view, a.geom_stride);
+        a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
+        a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+        a.counters = view_ptr(a.counters, view, a.tile_stride);
+        a.big_list = view_ptr(a.big_list, view, a.tile_stride);
+        a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+        a.entries = view_ptr(a.entries, view, a.entries_stride);
+        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+    }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int chunk = (a.ntiles + 1023) / 1024;
     const int begin = min(tid * chunk, a.ntiles), end = min(begin + chunk, a.ntiles);
@@ -145,6 +157,18 @@ __device__ __forceinline__ void emit_instance(const BinArgs& a, int tile, uint64
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
+    {   // view of this CTA: own geom / tile workspace and binning buffers
+        const int view = blockIdx.y;
+        a.depths = view_ptr(a.depths, view, a.geom_stride);
+        a.rects = view_ptr(a.rects, view, a.geom_stride);
+        a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
+        a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+        a.counters = view_ptr(a.counters, view, a.tile_stride);
+        a.big_list = view_ptr(a.big_list, view, a.tile_stride);
+        a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+        a.entries = view_ptr(a.entries, view, a.entries_stride);
+        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+    }
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0, ntiles = 0;
@@ -288,6 +312,18 @@ __global__ void __launch_bounds__(kSortSmallThreads) sort_small_kernel(BinArgs a
     __shared__ uint32_t s_hist[kSmallBuckets];
     __shared__ uint32_t s_start[kSmallBuckets + 1];
     __shared__ uint32_t s_misc[2 + 32];
+    {   // view of this CTA: own geom / tile workspace and binning buffers
+        const int view = blockIdx.y;
+        a.depths = view_ptr(a.depths, view, a.geom_stride);
+        a.rects = view_ptr(a.rects, view, a.geom_stride);
+        a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
+        a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+        a.counters = view_ptr(a.counters, view, a.tile_stride);
+        a.big_list = view_ptr(a.big_list, view, a.tile_stride);
+        a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+        a.entries = view_ptr(a.entries, view, a.entries_stride);
+        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+    }
     const uint2 r = a.ranges[blockIdx.x];
     const int n = (int)(r.y - r.x);
     const int tid = threadIdx.x;
@@ -314,6 +350,18 @@ __global__ void __launch_bounds__(1024) sort_big_kernel(BinArgs a) {
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_dyn + 2 * kBigSmemCap);
     uint32_t* s_start = s_hist + kBigBuckets;
     uint32_t* s_misc = s_start + kBigBuckets + 1;
+    {   // view of this CTA: own geom / tile workspace and binning buffers
+        const int view = blockIdx.y;
+        a.depths = view_ptr(a.depths, view, a.geom_stride);
+        a.rects = view_ptr(a.rects, view, a.geom_stride);
+        a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
+        a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+        a.counters = view_ptr(a.counters, view, a.tile_stride);
+        a.big_list = view_ptr(a.big_list, view, a.tile_stride);
+        a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+        a.entries = view_ptr(a.entries, view, a.entries_stride);
+        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+    }
     const int tid = threadIdx.x;
     const uint32_t nbig = a.counters[1];
     for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
@@ -333,37 +381,29 @@ __global__ void __launch_bounds__(1024) sort_big_kernel(BinArgs a) {
 }
 
 cudaError_t launch_tile_scan(const BinArgs& a, cudaStream_t stream) {
+    if (a.nviews <= 0) return cudaSuccess;
     prof_start(K_TILE_SCAN, stream);
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(a);
+    tile_scan_kernel<<<dim3(1, a.nviews), 1024, 0, stream>>>(a);
     prof_stop(K_TILE_SCAN, stream);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bin_and_sort(const BinArgs& a, cudaStream_t stream) {
-    static bool attr_set = false;
     const size_t big_smem = (size_t)2 * kBigSmemCap * sizeof(uint64_t) + (2 * kBigBuckets + 1 + 2 + 32 + 4) * sizeof(uint32_t);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)big_smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    if (a.P <= 0) return cudaSuccess;
+    if (a.P <= 0 || a.nviews <= 0) return cudaSuccess;
+    // the opt-in is per device (and cheap), so it is made on every call for the current device
+    cudaError_t e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem);
+    if (e != cudaSuccess) return e;
     prof_start(K_SCATTER, stream);
-    scatter_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+    scatter_kernel<<<dim3((a.P + 255) / 256, a.nviews), 256, 0, stream>>>(a);
     prof_stop(K_SCATTER, stream);
     prof_start(K_SORT_SMALL, stream);
-    sort_small_kernel<<<a.ntiles, kSortSmallThreads, 0, stream>>>(a);
+    sort_small_kernel<<<dim3(a.ntiles, a.nviews), kSortSmallThreads, 0, stream>>>(a);
     prof_stop(K_SORT_SMALL, stream);
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    // big tiles (> kSmallCap instances) are rare: a few persistent CTAs per view walk the list the scan produced
+    const int per_view = max(8, sm_count() / a.nviews);
     prof_start(K_SORT_BIG, stream);
-    sort_big_kernel<<<sms, 1024, big_smem, stream>>>(a);
+    sort_big_kernel<<<dim3(per_view, a.nviews), 1024, big_smem, stream>>>(a);
     prof_stop(K_SORT_BIG, stream);
     return cudaGetLastError();
 }

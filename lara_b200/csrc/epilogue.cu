@@ -38,7 +38,24 @@ __device__ __forceinline__ void point_at(const EpilogueArgs& a, int x, int y, si
     p[0] = r[0] + d * r[3]; p[1] = r[1] + d * r[4]; p[2] = r[2] + d * r[5];
 }
 
+// blockIdx.z = view: all images are stacked [V,C,H,W] (rays [V,H,W,6]); null pointers stay null
+__device__ __forceinline__ void select_view(EpilogueArgs& a) {
+    const size_t v = blockIdx.z;
+    if (v == 0) return;
+    const size_t npix = (size_t)a.W * a.H;
+    auto adv = [&](const float*& p, size_t n) { if (p) p += v * n; };
+    auto advm = [&](float*& p, size_t n) { if (p) p += v * n; };
+    adv(a.color, 3 * npix); adv(a.allmap, 8 * npix); adv(a.rays, 6 * npix);
+    a.viewmatrix += v * a.cam_stride;
+    advm(a.image, 3 * npix); advm(a.depth, npix); advm(a.acc, npix);
+    advm(a.rend_normal, 3 * npix); advm(a.depth_normal, 3 * npix); advm(a.dist, npix);
+    adv(a.g_image, 3 * npix); adv(a.g_depth, npix); adv(a.g_acc, npix);
+    adv(a.g_rend_normal, 3 * npix); adv(a.g_depth_normal, 3 * npix); adv(a.g_dist, npix);
+    advm(a.scratch, 3 * npix); advm(a.dL_dcolor, 3 * npix); advm(a.dL_dallmap, 8 * npix);
+}
+
 __global__ void __launch_bounds__(256) epilogue_fwd_kernel(EpilogueArgs a) {
+    select_view(a);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= a.W || y >= a.H) return;
@@ -71,6 +88,7 @@ __global__ void __launch_bounds__(256) epilogue_fwd_kernel(EpilogueArgs a) {
 
 // Backward pass 1: gradient wrt the (unnormalised) cross product of every interior pixel.
 __global__ void __launch_bounds__(256) epilogue_bwd_cross_kernel(EpilogueArgs a) {
+    select_view(a);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= a.W || y >= a.H) return;
@@ -128,6 +146,7 @@ __device__ __forceinline__ void add_center(const EpilogueArgs& a, int cx, int cy
 }
 
 __global__ void __launch_bounds__(256) epilogue_bwd_kernel(EpilogueArgs a) {
+    select_view(a);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= a.W || y >= a.H) return;
@@ -175,13 +194,13 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(EpilogueArgs a) {
 }
 
 cudaError_t launch_epilogue_fwd(const EpilogueArgs& a, cudaStream_t stream) {
-    const dim3 grid((a.W + 31) / 32, (a.H + 7) / 8);
+    const dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.nviews > 0 ? a.nviews : 1);
     epilogue_fwd_kernel<<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_epilogue_bwd(const EpilogueArgs& a, cudaStream_t stream) {
-    const dim3 grid((a.W + 31) / 32, (a.H + 7) / 8);
+    const dim3 grid((a.W + 31) / 32, (a.H + 7) / 8, a.nviews > 0 ? a.nviews : 1);
     if (a.g_depth_normal != nullptr && a.rays != nullptr) epilogue_bwd_cross_kernel<<<grid, 256, 0, stream>>>(a);
     epilogue_bwd_kernel<<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();

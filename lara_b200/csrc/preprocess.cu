@@ -101,6 +101,16 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
     const int idx = base + tid;
     const int nrows = min(256, a.P - base);
     const bool in_range = idx < a.P;
+    {   // view of this CTA (blockIdx.y): own camera, own geom / tile workspace, own radii row
+        const int view = blockIdx.y;
+        a.viewmatrix += (size_t)view * a.cam_stride;
+        a.campos += (size_t)view * a.cam_stride;
+        a.radii += (size_t)view * a.P;
+        a.rec = view_ptr(a.rec, view, a.geom_stride);
+        a.depths = view_ptr(a.depths, view, a.geom_stride);
+        a.rects = view_ptr(a.rects, view, a.geom_stride);
+        a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
+    }
 
     stage_rows(s_means, a.means3D + (size_t)base * 3, nrows * 3, tid, 256);
     if (tid < 16) s_view[tid] = __ldg(a.viewmatrix + tid);
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 }
 
 cudaError_t launch_preprocess_fwd(const PreprocessArgs& a, cudaStream_t stream) {
-    if (a.P <= 0) return cudaSuccess;
+    if (a.P <= 0 || a.nviews <= 0) return cudaSuccess;
     PreprocessArgs args = a;
     const size_t sh_bytes = (size_t)256 * 3 * a.M * sizeof(float);
     // stage SH rows through shared memory when they fit next to the static buffers
@@ -365,7 +375,7 @@ cudaError_t launch_preprocess_fwd(const PreprocessArgs& a, cudaStream_t stream) 
     const size_t dyn = args.stage_sh ? sh_bytes : 0;
     const int grid = (a.P + 255) / 256;
     prof_start(K_PREPROCESS_FWD, stream);
-    preprocess_fwd_kernel<<<grid, 256, dyn, stream>>>(args);
+    preprocess_fwd_kernel<<<dim3(grid, a.nviews), 256, dyn, stream>>>(args);
     prof_stop(K_PREPROCESS_FWD, stream);
     return cudaGetLastError();
 }

@@ -1,88 +1,138 @@
-// render_bwd.cu -- reverse-order per-pixel backward of the blend (K7).
+// render_bwd.cu -- reverse-order per-pixel backward of the blend (K7), two-phase form.
 // Replaces reference backward.cu:143-449 (renderCUDA backward).
 //
-// Same tiling as the forward: one CTA per 16x16 tile, one thread per pixel, the tile's
-// list walked back-to-front in shared-memory rounds of SRF_BATCH = 256 splats.  The reference emits
-// 10-16 global float atomics per (pixel, splat) pair, 256 threads hammering the same
-// <=18 addresses.  Here each warp first transposes-and-reduces the 16 partial
-// derivatives every contributing pair produces across its 32 lanes with a 16-shuffle
-// reduce-scatter (8+4+2+1+1; the two extra low-pass-branch values take a small butterfly
-// on the ~6 % of visits that have them), adds the warp totals into a per-batch shared-memory accumulator
-// (bank-conflict-free, 18 consecutive words per splat) and the CTA finally issues at
-// most five 128-bit vector reductions (red.global.add.v4.f32) per splat per tile.
-// Further savings the reference does not have:
-//   * the walk starts at the tile's last *used* list entry (max n_contrib over the
-//     tile) instead of the end of the list,
-//   * warp-uniform skips: entries beyond the warp's deepest contributor, and splats
-//     that no lane of the warp touches, cost no reduction traffic at all.
+// The backward of a (pixel, splat) pair has two very different halves:
+//   * a per-PIXEL sequential part -- transmittance T <- T/(1-alpha), the accum_rec recursions, the
+//     distortion / median terms (backward.cu:321-396) -- whose result is just three scalars per pair:
+//         w = alpha*T,   GdA = G * dL/dalpha,   dL/dz ;
+//   * a per-SPLAT reduction: every one of the 18 gradient values of the splat is a sum over pixels of
+//     terms LINEAR in (w, GdA, dL/dz) with coefficients that depend only on the pixel position and the
+//     splat's own record (backward.cu:398-446).
+// The reference does both per pixel and emits 10-16 global atomics per pair; round 1 of this repository
+// did both per pixel and reduced the 16 partials across the warp with a 16-shuffle reduce-scatter per
+// (warp, splat) visit -- ~100 of its ~300 warp instructions per visit, at 13/32 useful lanes.
+//
+// Here the two halves run in the layout that suits each (per warp, on its 8x4 pixel block, for groups of
+// 16 splats of the tile list that can touch the block):
+//   phase 1  lane = pixel.  Every lane walks ITS OWN hits (per-pixel octagon masks, as the forward does)
+//            back to front, does the sequential part and parks (w, GdA, dL/dz) in shared memory
+//            (3 floats per pair, XOR-swizzled so that both phases are bank-conflict free or nearly so).
+//   phase 2  lane = (splat, half block).  Every lane streams the 16 pixels of its half block, rebuilds the
+//            pixel-dependent coefficients from its splat's record held in registers, and accumulates the
+//            18 gradient values in registers -- no cross-lane reduction at all; the two halves are
+//            combined with one shuffle per value and go out as 4 (5) red.global.add.v4.f32 per
+//            (warp, splat).
+// What is kept from round 1: CTA per 16x16 tile in LPT order, the list walked back to front from the tile's
+// deepest used entry in staged rounds, warp-level octagon cull, packed fp32x2 arithmetic, MUFU.RCP.
 #include "surfel_common.cuh"
 #include "surfel_kernels.h"
 
 namespace srf {
 
-// MUFU.RCP, <= 1 ulp: the gradients need no bit-exactness (the forward-deciding chain in eval_pair()
-// keeps its IEEE divisions), and an IEEE reciprocal costs ~9 instructions plus a slow-path call.
+namespace {
+
+constexpr int kBwdGroup = 16;                 // splats per phase-1 / phase-2 group (X tile = 16 splats x 32 pixels)
+
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
-__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w)
-                 : "memory");
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-// Reduce-scatter of 16 per-lane values over the warp (16 -> 8 -> 4 -> 2 -> 1 values per lane, then the
-// two lanes of a pair are combined): every lane returns the warp total of value (lane >> 1) & 15.
-// 16 shuffles; a power of two, so there is no padding logic.
-__device__ __forceinline__ float warp_reduce_scatter16(const float (&v)[16], int lane) {
-    const unsigned full = 0xffffffffu;
-    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0, u1 = (lane & 2) != 0;
-    float a[8], b[4], c[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float keep = u4 ? v[8 + i] : v[i];
-        const float send = u4 ? v[i] : v[8 + i];
-        a[i] = keep + __shfl_xor_sync(full, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float keep = u3 ? a[4 + i] : a[i];
-        const float send = u3 ? a[i] : a[4 + i];
-        b[i] = keep + __shfl_xor_sync(full, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float keep = u2 ? b[2 + i] : b[i];
-        const float send = u2 ? b[i] : b[2 + i];
-        c[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-    float d = (u1 ? c[1] : c[0]) + __shfl_xor_sync(full, u1 ? c[0] : c[1], 2);
-    d += __shfl_xor_sync(full, d, 1);
-    return d;
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(SRF_CTA_THREADS, 768 / SRF_CTA_THREADS) render_bwd_kernel(RenderBwdArgs a) {
-    __shared__ float4 s_rec[SRF_REC_QUADS][SRF_BATCH];
-    __shared__ __align__(16) float s_grad[SRF_BATCH * SRF_GRAD_FLOATS];
-    __shared__ uint32_t s_id[SRF_BATCH];
-    __shared__ int s_touched[SRF_BATCH];
-    __shared__ int s_wmax[SRF_CTA_WARPS];
+__device__ __forceinline__ f32x2 shfl_xor2(f32x2 v, int m) {
+    return (f32x2)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
+}
+
+// Pair evaluation of the backward (same quantities as eval_pair(), forward.cu:353-398).  The backward only
+// has to agree with the forward's accept/reject decisions up to measure-zero ties and needs its values to
+// ~1e-6, so the two IEEE divisions and expf() of the forward-deciding chain become MUFU.RCP / MUFU.EX2
+// (<= 2 ulp).  A pair whose alpha sits within an ulp of 1/255 may be taken differently from the forward:
+// its weight is < 0.4 % of one pixel.
+struct PairBwd {
+    float sx, sy, depth, G, alpha;
+    bool lowpass, valid;
+};
+__device__ __forceinline__ void eval_pair_bwd(const float4 q0, const float4 q1, const float4 q2, const float pixx,
+                                              const float pixy, PairBwd& e) {
+    const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
+    const f32x2 pix2 = pk2(pixx, pixy);
+    const float2 klx = up2(fma2(pix2, bc2(Twx), pk2(-q0.x, -q0.y)));
+    const float2 kly = up2(fma2(pix2, bc2(Twy), pk2(-q0.z, -q0.w)));
+    const float2 klz = up2(fma2(pix2, bc2(Twz), pk2(-q1.x, -q1.y)));
+    const float pz = fmaf(klx.x, kly.y, -(kly.x * klx.y));
+    const float px = fmaf(kly.x, klz.y, -(klz.x * kly.y));
+    const float py = fmaf(klz.x, klx.y, -(klx.x * klz.y));
+    const float rpz = rcp_fast(pz);
+    e.sx = px * rpz; e.sy = py * rpz;
+    const float rho3d = fmaf(e.sx, e.sx, e.sy * e.sy);
+    const float2 d = up2(sub2(pk2(q2.y, q2.z), pix2));
+    const float rho2d = 2.0f * fmaf(d.x, d.x, d.y * d.y);
+    e.lowpass = !(rho3d <= rho2d);
+    const float rho = fminf(rho3d, rho2d);
+    const float depth3d = Twz + fmaf(Twx, e.sx, Twy * e.sy);
+    e.depth = e.lowpass ? Twz : depth3d;
+    // exp(-rho/2) = 2^(-rho * log2(e)/2)
+    e.G = ex2_fast(rho * -0.72134752044448170f);
+    e.alpha = fminf(0.99f, q2.w * e.G);
+    e.valid = (pz != 0.0f) && !(e.depth < SRF_NEAR_F) && !(rho < 0.0f) && !(e.alpha < 0.00392156862745098f);
+}
+
+template <int BATCH>
+struct BwdSmem {
+    static constexpr size_t rec = 0;                                                         // float4 [6][BATCH]
+    static constexpr size_t x = rec + sizeof(float4) * SRF_REC_QUADS * BATCH;                // float [warps][3][16][32]
+    static constexpr size_t pixA = x + sizeof(float) * SRF_CTA_WARPS * 3 * kBwdGroup * 32;   // float4 [256] dn0 dn1 dn2 dpix0
+    static constexpr size_t pixB = pixA + sizeof(float4) * SRF_CTA_THREADS;                  // float2 [256] dpix1 dpix2
+    static constexpr size_t list = pixB + sizeof(float2) * SRF_CTA_THREADS;                  // uint8 [warps][BATCH]
+    static constexpr size_t wmax = list + (size_t)SRF_CTA_WARPS * BATCH;                     // int [warps]
+    static constexpr size_t total = wmax + sizeof(int) * SRF_CTA_WARPS;
+};
+
+template <int BATCH, int MINB>
+__global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(RenderBwdArgs a) {
+    static_assert(BATCH <= 256, "hit lists are uint8");
+    extern __shared__ __align__(16) unsigned char smem[];
+    typedef BwdSmem<BATCH> L;
+    float4 (*s_rec)[BATCH] = reinterpret_cast<float4 (*)[BATCH]>(smem + L::rec);
+    float4* s_pixA = reinterpret_cast<float4*>(smem + L::pixA);
+    float2* s_pixB = reinterpret_cast<float2*>(smem + L::pixB);
+    int* s_wmax = reinterpret_cast<int*>(smem + L::wmax);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int tile = (int)a.tile_order[blockIdx.x / SRF_CTAS_PER_TILE];
-    const int gw = (int)(blockIdx.x % SRF_CTAS_PER_TILE) * SRF_CTA_WARPS + wid;   // which of the tile's eight 8x4 blocks
+    float* s_xw = reinterpret_cast<float*>(smem + L::x) + wid * (3 * kBwdGroup * 32);
+    uint8_t* s_listw = reinterpret_cast<uint8_t*>(smem + L::list) + wid * BATCH;
+
+    const int view = blockIdx.y;
+    const size_t npix = (size_t)a.W * a.H;
+    a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+    a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+    a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+    a.rec = view_ptr(a.rec, view, a.geom_stride);
+    a.bg += (size_t)view * a.cam_stride;
+    a.accum = view_ptr(a.accum, view, a.image_stride);
+    a.n_contrib = view_ptr(a.n_contrib, view, a.image_stride);
+    a.dL_dpix += (size_t)view * 3 * npix;
+    a.dL_dothers += (size_t)view * 8 * npix;
+    a.ggrad = view_ptr(a.ggrad, view, a.ggrad_stride);
+
+    const int tile = (int)a.tile_order[blockIdx.x];
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
-    tile_pixel(gw * 32 + lane, lx, ly);
+    tile_pixel(tid, lx, ly);
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
     const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
-    const size_t npix = (size_t)a.W * a.H;
     const size_t pix = (size_t)pyi * a.W + pxi;
-    const WarpRect wrect = make_warp_rect(txi, tyi, gw);
+    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -110,6 +160,9 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 768 / SRF_CTA_THREADS) render
     }
     const float final_A = 1.0f - T_final;
     const float bg_dot_dpixel = __ldg(a.bg + 0) * dpix0 + __ldg(a.bg + 1) * dpix1 + __ldg(a.bg + 2) * dpix2;
+    // the upstream values phase 2 multiplies w with, indexed by the pixel's thread id (= wid*32 + lane)
+    s_pixA[tid] = make_float4(dn0, dn1, dn2, dpix0);
+    s_pixB[tid] = make_float2(dpix1, dpix2);
 
     // deepest list entry any pixel of the warp / of the tile blended
     int wmax = last_contributor;
@@ -120,7 +173,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 768 / SRF_CTA_THREADS) render
     int n_eff = 0;
 #pragma unroll
     for (int w = 0; w < SRF_CTA_WARPS; ++w) n_eff = max(n_eff, s_wmax[w]);
-    const int rounds = (n_eff + SRF_BATCH - 1) / SRF_BATCH;
+    const int rounds = (n_eff + BATCH - 1) / BATCH;
 
     // accum_rec / last_* recursions of backward.cu:331-385, two channels per packed fp32x2 register:
     // (c0,c1) (c2,depth) (n0,n1) (n2,alpha); the matching upstream gradients are paired the same way
@@ -129,191 +182,251 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 768 / SRF_CTA_THREADS) render
     float last_alpha = 0.f;
     const f32x2 dpix01 = pk2(dpix0, dpix1), dpix2d = pk2(dpix2, dL_ddepth);
     const f32x2 dn01 = pk2(dn0, dn1), dn2a = pk2(dn2, dL_daccum);
-    const float npixy = -pixy;
     float last_dL_dT = 0.f;
+    const float nTfinal_bg = -T_final * bg_dot_dpixel;
+
+    // phase-2 identity of this lane
+    const int p2_i = lane & (kBwdGroup - 1), p2_h = lane >> 4;
 
     for (int b = 0; b < rounds; ++b) {
-        // stage batch b (back to front) and clear the accumulator rows this thread owns
-        const int pos_mine = n_eff - 1 - (b * SRF_BATCH + tid);
-        if (pos_mine >= 0) {
-            const uint32_t id = __ldg(a.point_list + range.x + pos_mine);
-            s_id[tid] = id;
-            const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
+        // ---- stage batch b (back to front: slot j holds list position n_eff-1-(b*BATCH+j))
+        __syncthreads();                                  // every warp is done with the previous batch's records
+        for (int jt = tid; jt < BATCH; jt += SRF_CTA_THREADS) {
+            const int pos = n_eff - 1 - (b * BATCH + jt);
+            if (pos >= 0) {
+                const uint32_t id = __ldg(a.point_list + range.x + pos);
+                const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
 #pragma unroll
-            for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][tid] = ldg4(r + k);
-        }
-        {
-            float4* g4 = reinterpret_cast<float4*>(s_grad + tid * SRF_GRAD_FLOATS);
-#pragma unroll
-            for (int k = 0; k < SRF_GRAD_FLOATS / 4; ++k) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            s_touched[tid] = 0;
+                for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][jt] = ldg4(r + k);
+                // the splat id rides in the (otherwise unused by the blend) clamp-bits word of q4
+                s_rec[4][jt].w = __uint_as_float(id);
+            }
         }
         __syncthreads();
+        const int cnt = min(BATCH, n_eff - b * BATCH);
 
-        const int cnt = min(SRF_BATCH, n_eff - b * SRF_BATCH);
-        const int nchunks = (cnt + 31) >> 5;
-        for (int c = 0; c < nchunks; ++c) {
-          // warp-level cull, 32 splats per ballot: skip splats behind the warp's deepest
-          // contributor and splats whose alpha >= 1/255 box misses the warp's 8x4 pixel block
-          unsigned hits;
-          {
-            const int jt = (c << 5) + lane;
+        // ---- warp-level cull: compacted list of the staged splats whose alpha >= 1/255 octagon can touch
+        // this warp's 8x4 block and that are not behind the warp's deepest contributor
+        int nh = 0;
+        for (int c = 0; c < cnt; c += 32) {
+            const int jt = c + lane;
             bool hit = false;
-            if (jt < cnt && n_eff - 1 - (b * SRF_BATCH + jt) < wmax) {
-                hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
-            }
-            hits = __ballot_sync(0xffffffffu, hit);
-          }
-          while (hits) {
-            const int j = (c << 5) + __ffs(hits) - 1;
-            hits &= hits - 1;
-            const int pos = n_eff - 1 - (b * SRF_BATCH + j);   // 0-based position in the tile list
-            bool contrib = inside && pos < last_contributor;
-            PairEval e;
-            const float4 q0 = s_rec[0][j], q1 = s_rec[1][j], q2 = s_rec[2][j];
-            if (contrib) {
-                eval_pair(q0, q1, q2, pixx, pixy, e);
-                contrib = e.valid;
-            }
-            if (!__any_sync(0xffffffffu, contrib)) continue;
+            if (jt < cnt && n_eff - 1 - (b * BATCH + jt) < wmax) hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hit) s_listw[nh + __popc(hits & ((1u << lane) - 1u))] = (uint8_t)jt;
+            nh += __popc(hits);
+        }
+        __syncwarp();
 
-            float g[18];
-#pragma unroll
-            for (int i = 0; i < 18; ++i) g[i] = 0.0f;
-            bool lowpass = false;
-
-            if (contrib) {
-                const float4 q3 = s_rec[3][j];
-                const float4 q4 = s_rec[4][j];
-                const float alpha = e.alpha, G = e.G, c_d = e.depth;
-                const float Twx = q1.z, Twy = q1.w;
-                const float opac = q2.w;
-
-                // one reciprocal serves T / (1-alpha) and the background term's T_final / (1-alpha)
-                const float r1ma = rcp_fast(1.0f - alpha);   // 1 - alpha >= 0.01
-                T = T * r1ma;
-                const float w = alpha * T;  // dchannel_dcolor
-                // accum_rec <- last_alpha * last + (1 - last_alpha) * accum_rec  (all eight channels)
-                const f32x2 la2 = bc2(last_alpha), oma2 = bc2(1.0f - last_alpha);
-                acc_c01 = fma2(last_c01, la2, mul2(acc_c01, oma2));
-                acc_c2d = fma2(last_c2d, la2, mul2(acc_c2d, oma2));
-                acc_n01 = fma2(last_n01, la2, mul2(acc_n01, oma2));
-                acc_n2a = fma2(last_n2a, la2, mul2(acc_n2a, oma2));
-                last_c01 = pk2(q4.x, q4.y); last_c2d = pk2(q4.z, c_d);
-                last_n01 = pk2(q3.x, q3.y); last_n2a = pk2(q3.z, 1.0f);
-                // dL_dalpha += (channel - accum_rec) * dL_dchannel over colour, depth, normal, alpha
-                f32x2 dsum = mul2(sub2(last_c01, acc_c01), dpix01);
-                dsum = fma2(sub2(last_c2d, acc_c2d), dpix2d, dsum);
-                dsum = fma2(sub2(last_n01, acc_n01), dn01, dsum);
-                dsum = fma2(sub2(last_n2a, acc_n2a), dn2a, dsum);
-                const float2 dsum_ = up2(dsum);
-                // w * upstream: colour and normal gradients of the splat, and w * dL_ddepth for dL_dz
-                const f32x2 w2 = bc2(w);
-                const float2 gc01 = up2(mul2(dpix01, w2)), gc2d = up2(mul2(dpix2d, w2)), gn01 = up2(mul2(dn01, w2));
-                g[SRF_G_DCOLOR + 0] = gc01.x; g[SRF_G_DCOLOR + 1] = gc01.y; g[SRF_G_DCOLOR + 2] = gc2d.x;
-                g[SRF_G_DNORMAL + 0] = gn01.x; g[SRF_G_DNORMAL + 1] = gn01.y; g[SRF_G_DNORMAL + 2] = w * dn2;
-
-                float dL_dz = gc2d.y, dL_dweight = 0.0f;
-                // distortion / median terms (backward.cu:350-368).  m_d = (FAR d - FAR NEAR)/((FAR-NEAR) d)
-                // = c1 - c2/d and d m_d/dd = c2/d^2; the reference evaluates both in double.  fp32 is
-                // enough here: the weight term below is stationary in m_d (its derivative is
-                // 2 (m_d A - D) ~ 0), and the gradients carry 1e-6 atomic-order noise anyway.
-                const float rcd = rcp_fast(c_d);             // depth >= 0.2
-                const float m_d = fmaf(-(float)(20.0 / 99.8), rcd, (float)(100.0 / 99.8));
-                const float dmd_dd = (float)(20.0 / 99.8) * rcd * rcd;
-                if (pos == median_contributor - 1) {
-                    dL_dz += dL_dmedian_depth;
-                    dL_dweight += dL_dmax_dweight;
-                }
-                dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
-                float dL_dalpha = (dsum_.x + dsum_.y) + (dL_dweight - last_dL_dT);
-                last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
-                const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
-                dL_dz += dL_dmd * dmd_dd;
-
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                // background term (backward.cu:391-396)
-                dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
-
-                const float dL_dG = opac * dL_dalpha;
-
-                if (e.rho3d <= e.rho2d) {
-                    // ray-splat branch: vjp through s = p.xy / p.z, p = k x l (backward.cu:405-435)
-                    const f32x2 S = pk2(e.sx, e.sy);
-                    const f32x2 dS = fma2(S, bc2(dL_dG * -G), mul2(pk2(Twx, Twy), bc2(dL_dz)));   // (dL_dsx, dL_dsy)
-                    const f32x2 dPxy = mul2(dS, bc2(rcp_fast(e.pz)));                           // (dL_dpx, dL_dpy)
-                    const float2 dp = up2(dPxy), dps = up2(mul2(dPxy, S));
-                    const float dpz = -(dps.x + dps.y);
-                    // dL_dk = l x dL_dp, dL_dl = dL_dp x k, as the pairs (dk.c, -dl.c) = the gradient record's layout:
-                    //   (dk.x,-dl.x) = (l.y,k.y) dpz - (l.z,k.z) dpy   and cyclic
-                    const f32x2 Sx = pk2(e.lx, e.kx), Sy = pk2(e.ly, e.ky), Sz = pk2(e.lz, e.kz);
-                    const float2 Dx = up2(fma2(Sy, bc2(dpz), mul2(Sz, bc2(-dp.y))));
-                    const float2 Dy = up2(fma2(Sz, bc2(dp.x), mul2(Sx, bc2(-dpz))));
-                    const float2 Dz = up2(fma2(Sx, bc2(dp.y), mul2(Sy, bc2(-dp.x))));
-                    g[SRF_G_DT + 0] = Dx.x; g[SRF_G_DT + 1] = Dx.y;
-                    g[SRF_G_DT + 2] = Dy.x; g[SRF_G_DT + 3] = Dy.y;
-                    g[SRF_G_DT + 4] = Dz.x; g[SRF_G_DT + 5] = Dz.y;
-                    // dL_dTw = pix.x dk + pix.y dl + dL_dz (s, 1)
-                    const float2 zs = up2(mul2(S, bc2(dL_dz)));
-                    g[SRF_G_DT + 6] = fmaf(pixx, Dx.x, fmaf(npixy, Dx.y, zs.x));
-                    g[SRF_G_DT + 7] = fmaf(pixx, Dy.x, fmaf(npixy, Dy.y, zs.y));
-                    g[SRF_G_DT + 8] = fmaf(pixx, Dz.x, fmaf(npixy, Dz.y, dL_dz));
-                } else {
-                    // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
-                    lowpass = true;
-                    const float2 gm = up2(mul2(pk2(e.dx, e.dy), bc2(dL_dG * (-2.0f * G))));
-                    g[SRF_G_DMEAN2D + 0] = gm.x;
-                    g[SRF_G_DMEAN2D + 1] = gm.y;
-                    g[SRF_G_DT + 8] = dL_dz;
-                }
-                g[SRF_G_DOPAC] = G * dL_dalpha;
-            }
-
-            // slots 0..15 in one power-of-two reduce-scatter; even lanes own value lane >> 1
+        for (int g0 = 0; g0 < nh; g0 += 32) {
+            // per-pixel hit words of 32 list entries: lane l rasterises splat g0+l over the block, the 32x32
+            // bit transpose hands lane p the word "which of these 32 splats can touch MY pixel"
+            uint32_t colword;
             {
-                float v16[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v16[i] = g[i];
-                const float total = warp_reduce_scatter16(v16, lane);
-                if ((lane & 1) == 0) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + (lane >> 1)], total);
-            }
-            // the two dL/dmean2D values exist only on low-pass lanes (~6 % of the visits)
-            if (__any_sync(0xffffffffu, lowpass)) {
-                float m0 = g[SRF_G_DMEAN2D + 0], m1 = g[SRF_G_DMEAN2D + 1];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
-                    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+                uint32_t m = 0;
+                if (g0 + lane < nh) {
+                    const int j = s_listw[g0 + lane];
+                    m = octagon_pixel_mask(s_rec[2][j], s_rec[5][j], wrect);
                 }
-                if (lane < 2) atomicAdd(&s_grad[j * SRF_GRAD_FLOATS + SRF_G_DMEAN2D + lane], lane ? m1 : m0);
+                colword = transpose32(m, lane);
             }
-            if (lane == 0) s_touched[j] = 1;
-          }
-        }
-        __syncthreads();
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int gbase = g0 + sub * kBwdGroup;
+                if (gbase >= nh) break;
+                const uint8_t* lst = s_listw + gbase;
 
-        // flush: one thread per staged splat, five 128-bit vector reductions
-        if (pos_mine >= 0 && s_touched[tid]) {
-            const float4* g4 = reinterpret_cast<const float4*>(s_grad + tid * SRF_GRAD_FLOATS);
-            float* dst = a.ggrad + (size_t)s_id[tid] * SRF_GRAD_FLOATS;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) red_add_v4(dst + 4 * k, g4[k]);
-            const float4 gm = g4[4];                     // dL/dmean2D: only if a low-pass pair touched the splat
-            if (gm.x != 0.0f || gm.y != 0.0f) red_add_v4(dst + 16, gm);
+                // ================= phase 1: lane = pixel =================
+                uint32_t bits = (colword >> (sub * kBwdGroup)) & 0xffffu;
+                if (last_contributor == 0) bits = 0;
+                uint32_t vbits = 0;
+                while (__any_sync(0xffffffffu, bits != 0)) {
+                    if (bits == 0) continue;
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int j = lst[i];
+                    const int pos = n_eff - 1 - (b * BATCH + j);   // 0-based position in the tile list
+                    if (pos >= last_contributor) continue;
+                    PairBwd e;
+                    eval_pair_bwd(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
+                    if (!e.valid) continue;
+                    const float4 q3 = s_rec[3][j];
+                    const float4 q4 = s_rec[4][j];
+                    const float alpha = e.alpha, c_d = e.depth;
+
+                    // one reciprocal serves T / (1-alpha) and the background term's T_final / (1-alpha)
+                    const float r1ma = rcp_fast(1.0f - alpha);   // 1 - alpha >= 0.01
+                    T = T * r1ma;
+                    const float w = alpha * T;
+                    // accum_rec <- last_alpha * last + (1 - last_alpha) * accum_rec  (all eight channels)
+                    const f32x2 la2 = bc2(last_alpha), oma2 = bc2(1.0f - last_alpha);
+                    acc_c01 = fma2(last_c01, la2, mul2(acc_c01, oma2));
+                    acc_c2d = fma2(last_c2d, la2, mul2(acc_c2d, oma2));
+                    acc_n01 = fma2(last_n01, la2, mul2(acc_n01, oma2));
+                    acc_n2a = fma2(last_n2a, la2, mul2(acc_n2a, oma2));
+                    last_c01 = pk2(q4.x, q4.y); last_c2d = pk2(q4.z, c_d);
+                    last_n01 = pk2(q3.x, q3.y); last_n2a = pk2(q3.z, 1.0f);
+                    // dL_dalpha += (channel - accum_rec) * dL_dchannel over colour, depth, normal, alpha
+                    f32x2 dsum = mul2(sub2(last_c01, acc_c01), dpix01);
+                    dsum = fma2(sub2(last_c2d, acc_c2d), dpix2d, dsum);
+                    dsum = fma2(sub2(last_n01, acc_n01), dn01, dsum);
+                    dsum = fma2(sub2(last_n2a, acc_n2a), dn2a, dsum);
+                    const float2 dsum_ = up2(dsum);
+
+                    float dL_dz = w * dL_ddepth, dL_dweight = 0.0f;
+                    // distortion / median terms (backward.cu:350-368).  m_d = (FAR d - FAR NEAR)/((FAR-NEAR) d)
+                    // = c1 - c2/d and d m_d/dd = c2/d^2; the reference evaluates both in double.  fp32 is
+                    // enough here: the weight term below is stationary in m_d (its derivative is
+                    // 2 (m_d A - D) ~ 0), and the gradients carry 1e-6 atomic-order noise anyway.
+                    const float rcd = rcp_fast(c_d);             // depth >= 0.2
+                    const float m_d = fmaf(-(float)(20.0 / 99.8), rcd, (float)(100.0 / 99.8));
+                    const float dmd_dd = (float)(20.0 / 99.8) * rcd * rcd;
+                    if (pos == median_contributor - 1) {
+                        dL_dz += dL_dmedian_depth;
+                        dL_dweight += dL_dmax_dweight;
+                    }
+                    dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
+                    float dL_dalpha = (dsum_.x + dsum_.y) + (dL_dweight - last_dL_dT);
+                    last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
+                    const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
+                    dL_dz += dL_dmd * dmd_dd;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    // background term (backward.cu:391-396)
+                    dL_dalpha = fmaf(nTfinal_bg, r1ma, dL_dalpha);
+
+                    // park the three scalars phase 2 needs; the sign of w carries the branch (w > 0 always)
+                    float* xp = s_xw + (i * 32 + (lane ^ i));
+                    xp[0] = e.lowpass ? -w : w;
+                    xp[kBwdGroup * 32] = e.G * dL_dalpha;
+                    xp[2 * kBwdGroup * 32] = dL_dz;
+                    vbits |= 1u << i;
+                }
+
+                __syncwarp();     // phase-1 stores to the X tile are visible to the whole warp
+
+                // ================= phase 2: lane = (splat i, half block h) =================
+                // valid-pair words: lane i (< 16) receives "which pixels contributed to splat i"
+                const uint32_t tw = transpose32(vbits, lane);
+                const uint32_t word = __shfl_sync(0xffffffffu, tw, p2_i);
+                const bool have = gbase + p2_i < nh;
+                const uint32_t mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
+                uint32_t tmask = __reduce_or_sync(0xffffffffu, mybits);
+                if (tmask == 0) continue;
+                const int j2 = have ? (int)lst[p2_i] : 0;
+                const float4 q0 = s_rec[0][j2], q1 = s_rec[1][j2], q2 = s_rec[2][j2];
+                const uint32_t splat_id = __float_as_uint(s_rec[4][j2].w);
+                const f32x2 nTu_x = pk2(-q0.x, -q0.y), nTu_y = pk2(-q0.z, -q0.w), nTu_z = pk2(-q1.x, -q1.y);
+                const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
+                const f32x2 Twxy = pk2(Twx, Twy), cen = pk2(q2.y, q2.z);
+                const float nopac = -q2.w;
+                // accumulators, laid out as the gradient record: (DT0,DT1) (DT2,DT3) (DT4,DT5) (DT6,DT7) (DT8,DOPAC)
+                // (DN0,DN1) (DN2,DC0) (DC1,DC2) (DM0,DM1)
+                f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull, A3 = 0ull, A4 = 0ull, A5 = 0ull, A6 = 0ull, A7 = 0ull, A8 = 0ull;
+                const float* xrow = s_xw + p2_i * 32;
+                const float ybase = wrect.ymin + (float)(2 * p2_h);
+                const int pbase = wid * 32 + 16 * p2_h;
+                while (tmask) {
+                    const int t = __ffs(tmask) - 1;
+                    tmask &= tmask - 1;
+                    if (!((mybits >> t) & 1u)) continue;
+                    const int p = t + 16 * p2_h;
+                    const float ppx = wrect.xmin + (float)(t & 7), ppy = ybase + (float)(t >> 3);
+                    const float* xp = xrow + (p ^ p2_i);
+                    const float ws = xp[0], GdA = xp[kBwdGroup * 32], dL_dz = xp[2 * kBwdGroup * 32];
+                    const float4 pa = s_pixA[pbase + t];
+                    const float2 pb = s_pixB[pbase + t];
+                    const float w = fabsf(ws);
+                    const f32x2 w2 = bc2(w);
+                    fma2_acc(A5, w2, pk2(pa.x, pa.y));      // dL/dnormal
+                    fma2_acc(A6, w2, pk2(pa.z, pa.w));      // dL/dnormal.z, dL/dcolor.r
+                    fma2_acc(A7, w2, pk2(pb.x, pb.y));      // dL/dcolor.gb
+                    const f32x2 pix2 = pk2(ppx, ppy);
+                    if (ws > 0.0f) {
+                        // ray-splat branch: vjp through s = p.xy / p.z, p = k x l (backward.cu:405-435)
+                        const float2 klx = up2(fma2(pix2, bc2(Twx), nTu_x));
+                        const float2 kly = up2(fma2(pix2, bc2(Twy), nTu_y));
+                        const float2 klz = up2(fma2(pix2, bc2(Twz), nTu_z));
+                        const float pz = fmaf(klx.x, kly.y, -(kly.x * klx.y));
+                        const float px = fmaf(kly.x, klz.y, -(klz.x * kly.y));
+                        const float py = fmaf(klz.x, klx.y, -(klx.x * klz.y));
+                        const float rpz = rcp_fast(pz);
+                        const f32x2 S = mul2(pk2(px, py), bc2(rpz));
+                        // dL_dG * -G = -opacity * (G dL_dalpha)
+                        const f32x2 dS = fma2(S, bc2(nopac * GdA), mul2(Twxy, bc2(dL_dz)));   // (dL_dsx, dL_dsy)
+                        const f32x2 dPxy = mul2(dS, bc2(rpz));                              // (dL_dpx, dL_dpy)
+                        const float2 dp = up2(dPxy), dps = up2(mul2(dPxy, S));
+                        const float dpz = -(dps.x + dps.y);
+                        // dL_dk = l x dL_dp, dL_dl = dL_dp x k, as the pairs (dk.c, -dl.c) = the record's layout
+                        const f32x2 Sx = pk2(klx.y, klx.x), Sy = pk2(kly.y, kly.x), Sz = pk2(klz.y, klz.x);
+                        const f32x2 Dx = fma2(Sy, bc2(dpz), mul2(Sz, bc2(-dp.y)));
+                        const f32x2 Dy = fma2(Sz, bc2(dp.x), mul2(Sx, bc2(-dpz)));
+                        const f32x2 Dz = fma2(Sx, bc2(dp.y), mul2(Sy, bc2(-dp.x)));
+                        A0 = add2(A0, Dx); A1 = add2(A1, Dy); A2 = add2(A2, Dz);
+                        // dL_dTw = pix.x dk + pix.y dl + dL_dz (s, 1)  (record holds -dl, hence -pix.y)
+                        const float2 Dx_ = up2(Dx), Dy_ = up2(Dy), Dz_ = up2(Dz);
+                        f32x2 tw67 = mul2(S, bc2(dL_dz));
+                        tw67 = fma2(bc2(ppx), pk2(Dx_.x, Dy_.x), tw67);
+                        tw67 = fma2(bc2(-ppy), pk2(Dx_.y, Dy_.y), tw67);
+                        A3 = add2(A3, tw67);
+                        const float tw8 = fmaf(ppx, Dz_.x, fmaf(-ppy, Dz_.y, dL_dz));
+                        A4 = add2(A4, pk2(tw8, GdA));
+                    } else {
+                        // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
+                        const f32x2 d = sub2(cen, pix2);
+                        fma2_acc(A8, d, bc2(2.0f * nopac * GdA));
+                        A4 = add2(A4, pk2(dL_dz, GdA));
+                    }
+                }
+                // combine the two half blocks and send the totals out: lanes of half 0 own record quads 0,1
+                // (and 4 if a low-pass pair touched the splat), lanes of half 1 own quads 2,3
+                A0 = add2(A0, shfl_xor2(A0, 16)); A1 = add2(A1, shfl_xor2(A1, 16));
+                A2 = add2(A2, shfl_xor2(A2, 16)); A3 = add2(A3, shfl_xor2(A3, 16));
+                A4 = add2(A4, shfl_xor2(A4, 16)); A5 = add2(A5, shfl_xor2(A5, 16));
+                A6 = add2(A6, shfl_xor2(A6, 16)); A7 = add2(A7, shfl_xor2(A7, 16));
+                A8 = add2(A8, shfl_xor2(A8, 16));
+                if (have && word != 0u) {
+                    float* dst = a.ggrad + (size_t)splat_id * SRF_GRAD_FLOATS;
+                    if (p2_h == 0) {
+                        const float2 a0 = up2(A0), a1 = up2(A1), a2 = up2(A2), a3 = up2(A3), a8 = up2(A8);
+                        red_add_v4(dst + 0, a0.x, a0.y, a1.x, a1.y);
+                        red_add_v4(dst + 4, a2.x, a2.y, a3.x, a3.y);
+                        if (a8.x != 0.0f || a8.y != 0.0f) red_add_v4(dst + 16, a8.x, a8.y, 0.0f, 0.0f);
+                    } else {
+                        const float2 a4 = up2(A4), a5 = up2(A5), a6 = up2(A6), a7 = up2(A7);
+                        red_add_v4(dst + 8, a4.x, a4.y, a5.x, a5.y);
+                        red_add_v4(dst + 12, a6.x, a6.y, a7.x, a7.y);
+                    }
+                }
+                __syncwarp();     // phase 1 of the next group overwrites the X tile
+            }
         }
-        // (the same thread re-zeroes its row and restages its slot at the top of the loop;
-        //  s_rec rows are protected by the barrier above)
     }
 }
 
+}  // namespace
+
+cudaError_t launch_render_bwd_v1(const RenderBwdArgs& a, cudaStream_t stream);
+
 cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
-    if (ntiles <= 0) return cudaSuccess;
+    if (ntiles <= 0 || a.nviews <= 0) return cudaSuccess;
+    const int variant = bwd_variant();
+    if (variant == 1) return launch_render_bwd_v1(a, stream);
     prof_start(K_RENDER_BWD, stream);
-    render_bwd_kernel<<<ntiles * SRF_CTAS_PER_TILE, SRF_CTA_THREADS, 0, stream>>>(a);
+    cudaError_t e = cudaSuccess;
+    const dim3 grid(ntiles, a.nviews);
+    if (variant == 3) {
+        constexpr int B = 128;
+        e = cudaFuncSetAttribute(render_bwd_kernel<B, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
+        if (e == cudaSuccess) render_bwd_kernel<B, 3><<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
+    } else {
+        constexpr int B = 256;
+        e = cudaFuncSetAttribute(render_bwd_kernel<B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
+        if (e == cudaSuccess) render_bwd_kernel<B, 2><<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
+    }
     prof_stop(K_RENDER_BWD, stream);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace srf

@@ -20,6 +20,19 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) rende
     __shared__ uint32_t s_mask[SRF_CTA_WARPS][SRF_BATCH_CHUNKS][32];   // [warp][chunk of 32 splats][lane]: per-pixel hit words
 
     const int tid = threadIdx.x;
+    {   // view of this CTA: per-view workspaces of identical layout, images stacked [V,C,H,W]
+        const int view = blockIdx.y;
+        const size_t npix_v = (size_t)a.W * a.H;
+        a.ranges = view_ptr(a.ranges, view, a.tile_stride);
+        a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
+        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
+        a.rec = view_ptr(a.rec, view, a.geom_stride);
+        a.bg += (size_t)view * a.cam_stride;
+        a.accum = view_ptr(a.accum, view, a.image_stride);
+        a.n_contrib = view_ptr(a.n_contrib, view, a.image_stride);
+        a.out_color += (size_t)view * 3 * npix_v;
+        a.out_others += (size_t)view * 8 * npix_v;
+    }
     const int tile = (int)a.tile_order[blockIdx.x / SRF_CTAS_PER_TILE];
     const int gw = (int)(blockIdx.x % SRF_CTAS_PER_TILE) * SRF_CTA_WARPS + (tid >> 5);   // which of the tile's eight 8x4 blocks
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
@@ -154,9 +167,9 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) rende
 
 cudaError_t launch_render_fwd(const RenderFwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
-    if (ntiles <= 0) return cudaSuccess;
+    if (ntiles <= 0 || a.nviews <= 0) return cudaSuccess;
     prof_start(K_RENDER_FWD, stream);
-    render_fwd_kernel<<<ntiles * SRF_CTAS_PER_TILE, SRF_CTA_THREADS, 0, stream>>>(a);
+    render_fwd_kernel<<<dim3(ntiles * SRF_CTAS_PER_TILE, a.nviews), SRF_CTA_THREADS, 0, stream>>>(a);
     prof_stop(K_RENDER_FWD, stream);
     return cudaGetLastError();
 }

@@ -14,7 +14,21 @@ from . import _lib
 from .rasterizer import ForwardState
 
 
-def unpack_state(state: ForwardState, P: int, H: int, W: int) -> Dict[str, torch.Tensor]:
+class _View:
+    """One view's slice of a batched ForwardState (V back-to-back workspaces)."""
+
+    def __init__(self, state: ForwardState, view: int):
+        V = state.nviews
+        def cut(t):
+            n = t.numel() // V
+            return t[view * n:(view + 1) * n]
+        self.geom, self.tile, self.image, self.point_list = cut(state.geom), cut(state.tile), cut(state.image), cut(state.point_list)
+        self.num_rendered = state.resolve()[view]
+
+
+def unpack_state(state: ForwardState, P: int, H: int, W: int, view: int = 0) -> Dict[str, torch.Tensor]:
+    if state.nviews > 1:
+        state = _View(state, view)
     lib = _lib.load()
     g_off, t_off, i_off = _lib.layout(lib, P, H, W)
     gx, gy = (W + 15) // 16, (H + 15) // 16

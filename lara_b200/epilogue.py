@@ -60,14 +60,62 @@ def epilogue_backward_raw(color, allmap, rays, viewmatrix, depth_ratio, gi, gd, 
     return d_color, d_allmap
 
 
+def epilogue_views_forward_raw(color, allmap, rays, cams, depth_ratio, image, depth, acc, rn, dn, dist):
+    """The fused forward over V stacked views in one launch: color [V,3,H,W], allmap [V,8,H,W], rays [V,H,W,6] or
+    None, cams [V,24] camera records (rasterizer.pack_cameras); outputs stacked [V,...] planar."""
+    lib = _lib.load()
+    V, H, W = int(color.shape[0]), int(color.shape[2]), int(color.shape[3])
+    dev = color.device
+    with _DeviceGuard(dev):
+        _lib.check(lib.srf_views_epilogue_forward(
+            _raw_stream(dev), V, H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays),
+            cams.data_ptr(), image.data_ptr(), depth.data_ptr(), acc.data_ptr(), rn.data_ptr(),
+            dn.data_ptr(), dist.data_ptr()), lib)
+
+
+def epilogue_views_backward_raw(color, allmap, rays, cams, depth_ratio, gi, gd, ga, grn, gdn, gds):
+    """Fused backward over V stacked views; returns (dL_dcolor [V,3,H,W], dL_dallmap [V,8,H,W])."""
+    lib = _lib.load()
+    V, H, W = int(color.shape[0]), int(color.shape[2]), int(color.shape[3])
+    dev = color.device
+    scratch = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
+    d_color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
+    d_allmap = torch.empty((V, 8, H, W), dtype=torch.float32, device=dev)
+    with _DeviceGuard(dev):
+        _lib.check(lib.srf_views_epilogue_backward(
+            _raw_stream(dev), V, H, W, float(depth_ratio), color.data_ptr(), allmap.data_ptr(), _p(rays),
+            cams.data_ptr(), _p(gi), _p(gd), _p(ga), _p(grn), _p(gdn), _p(gds),
+            scratch.data_ptr(), d_color.data_ptr(), d_allmap.data_ptr()), lib)
+    return d_color, d_allmap
+
+
+def _check_epilogue_inputs(color, allmap, rays, viewmatrix):
+    """fp32 / CUDA / same-device / shape checks: the kernel takes raw pointers (the reference's torch ops
+    would raise on their own)."""
+    dev = color.device
+    for name, t in (("rendered_image", color), ("allmap", allmap), ("world_view_transform", viewmatrix), ("rays", rays)):
+        if t is None:
+            continue
+        if not t.is_cuda or t.device != dev:
+            raise RuntimeError(f"render_img_epilogue: {name} must be a CUDA tensor on {dev}, got {t.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"render_img_epilogue: expected scalar type Float but found {t.dtype} for {name}")
+    H, W = int(color.shape[-2]), int(color.shape[-1])
+    if color.ndim != 3 or color.shape[0] != 3 or tuple(allmap.shape) != (8, H, W):
+        raise RuntimeError("render_img_epilogue: rendered_image must be [3,H,W] and allmap [8,H,W]")
+    if rays is not None and tuple(rays.shape) != (H, W, 6):
+        raise RuntimeError(f"render_img_epilogue: rays must be [H,W,6] = {(H, W, 6)}, got {tuple(rays.shape)}")
+    if viewmatrix.numel() != 16:
+        raise RuntimeError("render_img_epilogue: world_view_transform must have 16 elements")
+
+
 class _Epilogue(torch.autograd.Function):
     @staticmethod
     def forward(ctx, color, allmap, rays, viewmatrix, depth_ratio):
+        _check_epilogue_inputs(color, allmap, rays, viewmatrix)
         color = color.contiguous(); allmap = allmap.contiguous()
         viewmatrix = viewmatrix.contiguous()
         rays_c = rays.contiguous() if rays is not None else None
-        if color.dtype != torch.float32 or allmap.dtype != torch.float32 or not color.is_cuda:
-            raise RuntimeError("render_img_epilogue expects fp32 CUDA tensors")
         H, W = int(color.shape[1]), int(color.shape[2])
         dev = color.device
         def new(*shape):
@@ -97,30 +145,4 @@ def render_img_epilogue(rendered_image: torch.Tensor, allmap: torch.Tensor, rays
     return {
         f"image{prex}": image.permute(1, 2, 0), f"depth{prex}": depth.permute(1, 2, 0), f"acc_map{prex}": acc,
         f"rend_normal{prex}": rn.permute(1, 2, 0), f"depth_normal{prex}": dn.permute(1, 2, 0), f"rend_dist{prex}": dist,
-    }
-
-
-def render_img_epilogue_torch(rendered_image, allmap, rays, world_view_transform, depth_ratio=0.0, prex=""):
-    """Plain-torch restatement of renderer_2dgs.py:220-268 (+ depth_to_normal :74-89).
-
-    Test/measurement reference for the fused kernel -- this is what LaRa executes today."""
-    rendered_image = rendered_image.clamp(0, 1)
-    render_alpha = allmap[1:2]
-    render_normal = allmap[2:5]
-    render_normal = (render_normal.permute(1, 2, 0) @ (world_view_transform[:3, :3].T)).permute(2, 0, 1)
-    render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
-    render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
-    render_dist = allmap[6:7]
-    surf_depth = render_depth_expected * (1 - depth_ratio) + depth_ratio * render_depth_median
-    points = (rays[..., :3].reshape(-1, 3) + surf_depth.reshape(-1, 1) * rays[..., 3:].reshape(-1, 3)).reshape(
-        *surf_depth.shape[1:], 3)
-    output = torch.zeros_like(points)
-    dx = points[2:, 1:-1] - points[:-2, 1:-1]
-    dy = points[1:-1, 2:] - points[1:-1, :-2]
-    output[1:-1, 1:-1, :] = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
-    surf_normal = output.permute(2, 0, 1) * render_alpha.detach()
-    return {
-        f"image{prex}": rendered_image.permute(1, 2, 0), f"depth{prex}": surf_depth.permute(1, 2, 0),
-        f"acc_map{prex}": render_alpha.squeeze(0), f"rend_normal{prex}": render_normal.permute(1, 2, 0),
-        f"depth_normal{prex}": surf_normal.permute(1, 2, 0), f"rend_dist{prex}": render_dist.squeeze(0),
     }

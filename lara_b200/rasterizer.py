@@ -18,7 +18,9 @@ corresponding input was given (autograd discards them otherwise).
 from __future__ import annotations
 
 import os
-from typing import NamedTuple, Optional
+import threading
+import warnings
+from typing import List, NamedTuple, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -46,8 +48,8 @@ class GaussianRasterizationSettings(NamedTuple):
 # ---------------------------------------------------------------------------------
 
 _size_cache: dict = {}
-_capacity_hwm: dict = {}          # device index -> largest num_rendered seen (instances)
-_pinned_slots: dict = {}          # device index -> pinned uint32 readback slot
+_capacity_hwm: dict = {}          # device index -> largest num_rendered seen (instances per view)
+_lock = threading.Lock()          # autograd calls backward() from another host thread
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -84,35 +86,12 @@ def _blob(nbytes: int, device) -> torch.Tensor:
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def _slot(device: torch.device) -> torch.Tensor:
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    s = _pinned_slots.get(idx)
-    if s is None:
-        s = torch.zeros(1, dtype=torch.int32).pin_memory()
-        _pinned_slots[idx] = s
-    return s
-
-
-_events: dict = {}
-
-
-def _event(device: torch.device) -> "torch.cuda.Event":
-    """One reusable CUDA event per device (the forward waits on it before returning)."""
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    e = _events.get(idx)
-    if e is None:
-        # The forward waits on this event for num_rendered.  Blocking (sleeping) wait by default: the GPU boxes
-        # run under a CPU quota (16 CPUs for a 1-GPU box although 128 are visible), so a rank that spins takes
-        # cycles from the other ranks' host threads; measured at N=1: 1726 vs 1724 views/s (no difference).
-        # SRF_SPIN_EVENT_WAIT=1 restores the spinning wait.
-        e = torch.cuda.Event(blocking=os.environ.get("SRF_SPIN_EVENT_WAIT", "0") != "1")
-        _events[idx] = e
-    return e
+def _dev_index(device: torch.device) -> int:
+    return device.index if device.index is not None else torch.cuda.current_device()
 
 
 def _raw_stream(device: torch.device) -> int:
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    return torch._C._cuda_getCurrentRawStream(idx)
+    return torch._C._cuda_getCurrentRawStream(_dev_index(device))
 
 
 class _DeviceGuard:
@@ -134,26 +113,179 @@ class _DeviceGuard:
 
 
 def initial_capacity(P: int, device: torch.device) -> int:
-    """Optimistic instance capacity for the binning buffers of a forward call."""
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    hwm = _capacity_hwm.get(idx, 0)
+    """Optimistic per-view instance capacity for the binning buffers of a forward call."""
+    hwm = _capacity_hwm.get(_dev_index(device), 0)
     return max(int(hwm * 1.25) + 1024, 8 * P, 1 << 16)
 
 
 def _note_rendered(R: int, device: torch.device) -> None:
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    if R > _capacity_hwm.get(idx, 0):
-        _capacity_hwm[idx] = R
+    idx = _dev_index(device)
+    with _lock:
+        if R > _capacity_hwm.get(idx, 0):
+            _capacity_hwm[idx] = R
 
 
-class ForwardState(NamedTuple):
-    """What a forward leaves behind for the backward (the reference's three blobs)."""
-    geom: torch.Tensor
-    tile: torch.Tensor
-    image: torch.Tensor
-    point_list: torch.Tensor
-    capacity: int
-    num_rendered: int
+# ---------------------------------------------------------------------------------
+# num_rendered read-back.  The reference blocks the host on a cudaMemcpy in the middle of every
+# forward (rasterizer_impl.cu:282).  Here the count travels to a pinned slot asynchronously and is
+# only *needed* by the host to verify the optimistic instance capacity, so the wait is deferred:
+# a forward returns without touching the event; the count is resolved the first time somebody asks
+# for it (ForwardState.num_rendered / ctx.num_rendered), when the backward of that forward starts, or
+# -- without blocking -- at the next forward on the device once its event has completed.  If the
+# capacity turns out to have been too small (first call of a much larger scene), stage 2 is re-run in
+# place with larger buffers and a RuntimeWarning says that results consumed in between were stale.
+# raster_settings.debug=True (the reference's "synchronise and check" switch) or
+# SRF_SYNC_NUM_RENDERED=1 restore the eager wait inside the forward.
+# ---------------------------------------------------------------------------------
+
+_SLOT_WORDS = 32
+_readback_pool: dict = {}         # device index -> list of free (pinned int32[_SLOT_WORDS], event)
+_pending: dict = {}               # device index -> list of unresolved _Pending
+
+
+def _take_readback(device: torch.device, words: int):
+    idx = _dev_index(device)
+    with _lock:
+        free = _readback_pool.setdefault(idx, [])
+        for k, (slot, ev) in enumerate(free):
+            if slot.numel() >= words:
+                return free.pop(k)
+    slot = torch.zeros(max(words, _SLOT_WORDS), dtype=torch.int32).pin_memory()
+    # blocking (sleeping) wait: the GPU boxes run under a CPU quota, a spinning rank steals cycles from its peers
+    ev = torch.cuda.Event(blocking=os.environ.get("SRF_SPIN_EVENT_WAIT", "0") != "1")
+    return slot, ev
+
+
+def _give_readback(device: torch.device, rb) -> None:
+    with _lock:
+        _readback_pool.setdefault(_dev_index(device), []).append(rb)
+
+
+def _eager_sync(debug: bool) -> bool:
+    return bool(debug) or os.environ.get("SRF_SYNC_NUM_RENDERED", "0") == "1"
+
+
+class _Pending:
+    """An enqueued forward whose instance counts have not been read back yet."""
+
+    def __init__(self, device, rb, nviews: int, capacity: int, rerun):
+        self.device, self.rb, self.V, self.capacity, self.rerun = device, rb, nviews, capacity, rerun
+        self.counts: Optional[List[int]] = None
+        self.lock = threading.Lock()
+
+    def ready(self) -> bool:
+        return self.counts is not None or self.rb[1].query()
+
+    def resolve(self, stale_ok: bool = False) -> List[int]:
+        with self.lock:
+            if self.counts is not None:
+                return self.counts
+            slot, ev = self.rb
+            ev.synchronize()
+            counts = [int(x) & 0xFFFFFFFF for x in slot[:self.V].tolist()]
+            _give_readback(self.device, self.rb)
+            self.rb = None
+            R = max(counts) if counts else 0
+            _note_rendered(R, self.device)
+            if R > self.capacity:
+                self.rerun(int(R * 1.25) + 1024)
+                if not stale_ok:
+                    warnings.warn(
+                        f"surfel rasterizer: {R} instances exceeded the optimistic capacity {self.capacity}; the forward "
+                        "was re-run in place, but work enqueued between the two runs read incomplete images. Set "
+                        "raster_settings.debug=True or SRF_SYNC_NUM_RENDERED=1 to verify the capacity inside every forward.",
+                        RuntimeWarning, stacklevel=3)
+            self.rerun = None
+            self.counts = counts
+        with _lock:
+            lst = _pending.get(_dev_index(self.device))
+            if lst and self in lst:
+                lst.remove(self)
+        return counts
+
+
+def _drain_ready(device: torch.device) -> None:
+    """Resolve, without blocking, the pending forwards of this device whose read-back has landed."""
+    with _lock:
+        lst = list(_pending.get(_dev_index(device), ()))
+    for p in lst:
+        if p.ready():
+            p.resolve()
+
+
+class LazyCount:
+    """int-like view of a forward's num_rendered that waits for the read-back only when asked."""
+
+    def __init__(self, pending: "_Pending", view: int = 0):
+        self._p, self._v = pending, view
+
+    def __int__(self):
+        return self._p.resolve()[self._v]
+
+    __index__ = __int__
+
+    def __eq__(self, o):
+        return int(self) == o
+
+    def __hash__(self):
+        return hash(int(self))
+
+    def __repr__(self):
+        return str(int(self))
+
+
+class ForwardState:
+    """What a forward leaves behind for the backward (the reference's three blobs).  For the batched
+    entry the workspaces hold V per-view workspaces back to back."""
+    __slots__ = ("geom", "tile", "image", "point_list", "capacity", "nviews", "_pending", "_counts")
+
+    def __init__(self, geom, tile, image, point_list, capacity, num_rendered=0, nviews: int = 1, pending=None):
+        self.geom, self.tile, self.image, self.point_list = geom, tile, image, point_list
+        self.capacity, self.nviews = capacity, nviews
+        self._pending = pending
+        self._counts = None if pending is not None else ([int(num_rendered)] * nviews
+                                                         if not isinstance(num_rendered, (list, tuple)) else list(num_rendered))
+
+    def resolve(self) -> List[int]:
+        if self._counts is None:
+            self._counts = self._pending.resolve()
+            self._pending = None
+        return self._counts
+
+    @property
+    def num_rendered(self):
+        c = self.resolve()
+        return c[0] if self.nviews == 1 else list(c)
+
+
+def _launch_forward(device, lib, nviews, P, capacity, debug, call_pre, call_render, state_blobs, alloc_binning):
+    """Common enqueue sequence of the per-view and the batched forward:
+    stage 1 (preprocess + tile scan + async count read-back) -> event -> stage 2 with an optimistic capacity."""
+    _drain_ready(device)
+    rb = _take_readback(device, nviews)
+    slot, ev = rb
+    call_pre(slot.data_ptr())
+    ev.record()
+    geom, tile, image = state_blobs
+    entries, point_list = alloc_binning(capacity)
+    call_render(capacity, entries, point_list)
+    state = ForwardState(geom, tile, image, point_list, capacity, nviews=nviews)
+
+    def rerun(new_capacity: int):
+        with _DeviceGuard(device):
+            e2, pl2 = alloc_binning(new_capacity)
+            call_render(new_capacity, e2, pl2)
+            state.point_list, state.capacity = pl2, new_capacity
+
+    pend = _Pending(device, rb, nviews, capacity, rerun)
+    state._pending, state._counts = pend, None
+    if _eager_sync(debug):
+        pend.resolve(stale_ok=True)      # nothing has consumed the outputs yet
+        state.resolve()
+    else:
+        with _lock:
+            _pending.setdefault(_dev_index(device), []).append(pend)
+    return state
 
 
 def forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
@@ -198,39 +330,115 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
     viewm = raster_settings.viewmatrix
     projm = raster_settings.projmatrix
     campos = raster_settings.campos
-    slot = _slot(device)
-    _lib.check(lib.srf_forward_preprocess(
-        sptr, P, int(raster_settings.sh_degree), M,
-        _ptr(means3D), _ptr(shs), _ptr(colors_precomp),
-        _ptr(opacities), _ptr(scales), float(raster_settings.scale_modifier),
-        _ptr(rotations), _ptr(transMat_precomp),
-        _ptr(viewm), _ptr(projm), _ptr(campos),
-        float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
-        1 if raster_settings.prefiltered else 0,
-        radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot.data_ptr(), 1 if raw_activations else 0), lib)
-    ev = _event(device)
-    ev.record()
+
+    def call_pre(slot_ptr):
+        _lib.check(lib.srf_forward_preprocess(
+            sptr, P, int(raster_settings.sh_degree), M,
+            _ptr(means3D), _ptr(shs), _ptr(colors_precomp),
+            _ptr(opacities), _ptr(scales), float(raster_settings.scale_modifier),
+            _ptr(rotations), _ptr(transMat_precomp),
+            _ptr(viewm), _ptr(projm), _ptr(campos),
+            float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
+            1 if raster_settings.prefiltered else 0,
+            radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot_ptr, 1 if raw_activations else 0), lib)
+
+    def alloc_binning(capacity):
+        ent_b, pl_b = _lib.binning_sizes(lib, capacity)
+        return _blob(ent_b, device), _blob(pl_b, device)
+
+    def call_render(capacity, entries, point_list):
+        # (re-)enqueued on whatever stream is current: a deferred re-run happens on the caller's stream
+        _lib.check(lib.srf_forward_render(
+            _raw_stream(device), P, H, W, capacity, geom.data_ptr(), tile.data_ptr(),
+            entries.data_ptr(), point_list.data_ptr(), image.data_ptr(),
+            _ptr(bg), color.data_ptr(), allmap.data_ptr()), lib)
 
     # Optimistic capacity: stage 2 is enqueued before num_rendered is known on the host, so
     # the GPU never idles behind the read-back; an overflow (rare) just re-runs stage 2.
-    capacity = initial_capacity(P, device)
-    while True:
-        ent_b, pl_b = _lib.binning_sizes(lib, capacity)
-        entries = _blob(ent_b, device)
-        point_list = _blob(pl_b, device)
-        _lib.check(lib.srf_forward_render(
-            sptr, P, H, W, capacity, geom.data_ptr(), tile.data_ptr(),
-            entries.data_ptr(), point_list.data_ptr(), image.data_ptr(),
-            _ptr(bg), color.data_ptr(), allmap.data_ptr()), lib)
-        ev.synchronize()
-        R = int(slot.item()) & 0xFFFFFFFF
-        if R <= capacity:
-            break
-        capacity = int(R * 1.25) + 1024
-    _note_rendered(R, device)
+    state = _launch_forward(device, lib, 1, P, initial_capacity(P, device), raster_settings.debug,
+                            call_pre, call_render, (geom, tile, image), alloc_binning)
     if raster_settings.debug:
         torch.cuda.synchronize(device)
-    return color, allmap, radii, ForwardState(geom, tile, image, point_list, capacity, R)
+    return color, allmap, radii, state
+
+
+def pack_cameras(settings_list: Sequence[GaussianRasterizationSettings], device) -> torch.Tensor:
+    """[V, SRF_CAM_FLOATS] device tensor of per-view camera records (viewmatrix | campos | bg | pad) built
+    from per-view settings with ONE cat kernel (the tensors are already on the device, as LaRa's MiniCam
+    produces them, lightning/utils.py:33-48)."""
+    parts = []
+    pad = torch.zeros(_lib.CAM_FLOATS - 22, dtype=torch.float32, device=device)
+    for rs in settings_list:
+        parts += [rs.viewmatrix.reshape(16), rs.campos.reshape(3), rs.bg.reshape(3), pad]
+    return torch.cat(parts).view(len(settings_list), _lib.CAM_FLOATS)
+
+
+def forward_views_raw(means3D, shs, colors_precomp, opacities, scales, rotations, transMat_precomp,
+                      cams: torch.Tensor, tanfovx: float, tanfovy: float, H: int, W: int, sh_degree: int,
+                      prefiltered: bool = False, debug: bool = False, raw_activations: bool = False):
+    """All V views of one Gaussian set in ONE launch set (srf_views_*): every kernel carries a view
+    dimension.  `cams` is the [V, 24] device tensor of camera records (pack_cameras).
+    Returns (color [V,3,H,W], allmap [V,8,H,W], radii [V,P], ForwardState with V back-to-back workspaces)."""
+    with _DeviceGuard(means3D.device):
+        lib = _lib.load()
+        device = means3D.device
+        V, P = int(cams.shape[0]), int(means3D.shape[0])
+        M = int(shs.shape[1]) if shs is not None else 0
+        if cams.dtype != torch.float32 or not cams.is_cuda or cams.shape[1] != _lib.CAM_FLOATS or not cams.is_contiguous():
+            raise RuntimeError(f"cams must be a contiguous float32 CUDA tensor [V,{_lib.CAM_FLOATS}]")
+        color = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
+        allmap = torch.empty((V, 8, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((V, P), dtype=torch.int32, device=device)
+        geom_b, tile_b, image_b, _, _, _ = _lib.views_sizes(lib, V, P, H, W, 0)
+        blob = _blob(geom_b + tile_b + image_b, device)
+        geom, tile, image = blob[:geom_b], blob[geom_b:geom_b + tile_b], blob[geom_b + tile_b:]
+        if P == 0:
+            color.zero_(); allmap.zero_(); tile.zero_(); image.zero_()
+            pl = torch.empty((0,), dtype=torch.int32, device=device)
+            return color, allmap, radii, ForwardState(geom, tile, image, pl, 0, 0, nviews=V)
+        sptr = _raw_stream(device)
+
+        def call_pre(slot_ptr):
+            _lib.check(lib.srf_views_forward_preprocess(
+                sptr, V, P, int(sh_degree), M, _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities),
+                _ptr(scales), _ptr(rotations), _ptr(transMat_precomp), cams.data_ptr(), float(tanfovx), float(tanfovy),
+                H, W, 1 if prefiltered else 0, radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot_ptr,
+                1 if raw_activations else 0), lib)
+
+        def alloc_binning(capacity):
+            _, _, _, ent_b, pl_b, _ = _lib.views_sizes(lib, V, P, H, W, capacity)
+            return _blob(ent_b, device), _blob(pl_b, device)
+
+        def call_render(capacity, entries, point_list):
+            _lib.check(lib.srf_views_forward_render(
+                _raw_stream(device), V, P, H, W, capacity, geom.data_ptr(), tile.data_ptr(), entries.data_ptr(),
+                point_list.data_ptr(), image.data_ptr(), cams.data_ptr(), color.data_ptr(), allmap.data_ptr()), lib)
+
+        state = _launch_forward(device, lib, V, P, initial_capacity(P, device), debug, call_pre, call_render,
+                                (geom, tile, image), alloc_binning)
+        if debug:
+            torch.cuda.synchronize(device)
+        return color, allmap, radii, state
+
+
+def _grad_outputs(P, M, device, shs, colors_precomp, transMat_precomp, out, accumulate, need_means2D):
+    shapes = {"means3D": (P, 3), "means2D": (P, 3) if need_means2D else None,
+              "sh": (P, M, 3) if shs is not None else None,
+              "colors_precomp": (P, 3) if colors_precomp is not None else None,
+              "opacities": (P, 1), "scales": (P, 2), "rotations": (P, 4),
+              "cov3Ds_precomp": (P, 9) if transMat_precomp is not None else None}
+    g = {k: out.get(k) for k in shapes}
+    missing = [k for k, shp in shapes.items() if shp is not None and g[k] is None]
+    if missing:
+        # one allocation for all gradients that the caller did not supply (16-byte aligned segments)
+        sizes = [(-(-int(torch.Size(shapes[k]).numel()) // 4)) * 4 for k in missing]
+        flat = (torch.zeros if accumulate else torch.empty)(sum(sizes), dtype=torch.float32, device=device)
+        o = 0
+        for k, sz in zip(missing, sizes):
+            n = int(torch.Size(shapes[k]).numel())
+            g[k] = flat[o:o + n].view(shapes[k])
+            o += sz
+    return g
 
 
 def backward_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scales, rotations,
@@ -257,26 +465,10 @@ def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations,
     P = int(means3D.shape[0])
     device = means3D.device
     M = int(shs.shape[1]) if shs is not None else 0
-    out = out or {}
-
-    shapes = {"means3D": (P, 3), "means2D": (P, 3) if need_means2D else None,
-              "sh": (P, M, 3) if shs is not None else None,
-              "colors_precomp": (P, 3) if colors_precomp is not None else None,
-              "opacities": (P, 1), "scales": (P, 2), "rotations": (P, 4),
-              "cov3Ds_precomp": (P, 9) if transMat_precomp is not None else None}
-    g = {k: out.get(k) for k in shapes}
-    missing = [k for k, shp in shapes.items() if shp is not None and g[k] is None]
-    if missing:
-        # one allocation for all gradients that the caller did not supply (16-byte aligned segments)
-        sizes = [(-(-int(torch.Size(shapes[k]).numel()) // 4)) * 4 for k in missing]
-        flat = (torch.zeros if accumulate else torch.empty)(sum(sizes), dtype=torch.float32, device=device)
-        o = 0
-        for k, sz in zip(missing, sizes):
-            n = int(torch.Size(shapes[k]).numel())
-            g[k] = flat[o:o + n].view(shapes[k])
-            o += sz
+    g = _grad_outputs(P, M, device, shs, colors_precomp, transMat_precomp, out or {}, accumulate, need_means2D)
     if P == 0:
         return g
+    state.resolve()                 # capacity verified (re-run if it overflowed) before the lists are walked again
     _, _, _, scratch_b = _sizes(lib, P, H, W)
     scratch = _blob(scratch_b, device)
     sptr = _raw_stream(device)
@@ -296,6 +488,38 @@ def _backward_raw(state, radii, means3D, shs, colors_precomp, scales, rotations,
     if raster_settings.debug:
         torch.cuda.synchronize(device)
     return g
+
+
+def backward_views_raw(state: ForwardState, radii, means3D, shs, colors_precomp, scales, rotations, transMat_precomp,
+                       cams: torch.Tensor, tanfovx: float, tanfovy: float, H: int, W: int, sh_degree: int,
+                       grad_color, grad_allmap, *, out: Optional[dict] = None, accumulate: bool = False,
+                       need_means2D: bool = False, raw_activations: bool = False, debug: bool = False):
+    """Backward of forward_views_raw: grad_color [V,3,H,W], grad_allmap [V,8,H,W]; the per-Gaussian backward
+    sums the V views in registers and writes (accumulate: adds into) every parameter-gradient row once."""
+    with _DeviceGuard(means3D.device):
+        lib = _lib.load()
+        device = means3D.device
+        V, P = int(cams.shape[0]), int(means3D.shape[0])
+        M = int(shs.shape[1]) if shs is not None else 0
+        g = _grad_outputs(P, M, device, shs, colors_precomp, transMat_precomp, out or {}, accumulate, need_means2D)
+        if P == 0:
+            return g
+        state.resolve()
+        scratch_b = _lib.views_sizes(lib, V, P, H, W, 0)[5]
+        scratch = _blob(scratch_b, device)
+        _lib.check(lib.srf_views_backward(
+            _raw_stream(device), V, P, int(sh_degree), M, H, W, state.capacity, cams.data_ptr(),
+            _ptr(means3D), _ptr(shs), 1 if colors_precomp is not None else 0,
+            _ptr(scales), _ptr(rotations), 1 if transMat_precomp is not None else 0,
+            float(tanfovx), float(tanfovy), radii.data_ptr(),
+            state.geom.data_ptr(), state.tile.data_ptr(), state.point_list.data_ptr(), state.image.data_ptr(),
+            grad_color.data_ptr(), grad_allmap.data_ptr(), scratch.data_ptr(), 1 if accumulate else 0,
+            _ptr(g["means3D"]), _ptr(g["means2D"]), _ptr(g["sh"]), _ptr(g["colors_precomp"]),
+            _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), _ptr(g["cov3Ds_precomp"]),
+            1 if raw_activations else 0), lib)
+        if debug:
+            torch.cuda.synchronize(device)
+        return g
 
 
 def _dump_snapshot(path: str, items) -> None:
@@ -399,8 +623,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
             raise
         ctx.raster_settings = raster_settings
-        ctx.num_rendered = state.num_rendered
-        ctx.capacity = state.capacity
+        ctx.state = state
+        # an int for an eager forward, else an int-like object that waits for the read-back when asked
+        ctx.num_rendered = state.num_rendered if state._pending is None else LazyCount(state._pending)
         ctx.present = (sh_c is not None, colors_c is not None, scales_c is not None,
                        rot_c is not None, cov_c is not None)
         ctx.opac_shape = tuple(opacities.shape)
@@ -410,16 +635,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             colors_c if colors_c is not None else dummy, means3D_c,
             scales_c if scales_c is not None else dummy, rot_c if rot_c is not None else dummy,
             cov_c if cov_c is not None else dummy, radii, sh_c if sh_c is not None else dummy,
-            state.geom, state.point_list, state.image, state.tile)
+            state.geom, state.image, state.tile)
         ctx.mark_non_differentiable(radii)
         return color, radii, allmap
 
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
         rs = ctx.raster_settings
-        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, point_list, image, tile) = ctx.saved_tensors
+        (colors_c, means3D, scales, rotations, cov_c, radii, sh, geom, image, tile) = ctx.saved_tensors
         has_sh, has_col, has_sc, has_rot, has_cov = ctx.present
-        state = ForwardState(geom, tile, image, point_list, ctx.capacity, ctx.num_rendered)
+        state = ctx.state     # holds the index list (replaced if a deferred capacity check re-ran stage 2)
         grad_out_color = _f32c(grad_out_color, "dL_dout_color")
         grad_depth = _f32c(grad_depth, "dL_dout_others")
         try:

@@ -2,10 +2,10 @@
 
 Every target view of a scene is an independent forward+backward over the same read-only
 Gaussian set; only the parameter gradients sum across views.  One process per GPU
-(``torch.distributed``, NCCL over NVLink): rank r renders views ``r, r+G, r+2G, ...``,
-the backward kernel *accumulates* each view's parameter gradients straight into one flat
-fp32 buffer (segment-major: means3D | sh | opacity | scales | rotations), and a single
-``all_reduce(sum)`` of that buffer finishes the step.  Images / aux maps stay on the rank
+(``torch.distributed``, NCCL over NVLink): rank r renders views ``r, r+G, r+2G, ...`` in ONE
+launch set (``srf_views_*``), the per-Gaussian backward sums the rank's views in registers and adds
+the result into one flat fp32 buffer (segment-major: means3D | sh | opacity | scales | rotations),
+and a single ``all_reduce(sum)`` of that buffer finishes the step.  Images / aux maps stay on the rank
 that owns the view.  The reference has nothing like this (it is single-GPU; LaRa only
 data-parallelises over scenes), so there is no reference API to mirror here -- this is an
 additional entry point next to the unchanged per-view one.
@@ -57,20 +57,21 @@ class GradBuffer:
 
 
 def render_views(params: Dict[str, torch.Tensor], settings_list: Sequence[R.GaussianRasterizationSettings],
-                 upstream: Callable[[int, torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
+                 upstream: Optional[Callable[[int, torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]]],
                  grads: Optional[GradBuffer] = None, view_ids: Optional[Sequence[int]] = None,
-                 raster_fn=None, streams: int = 1, _pool: Optional[dict] = None):
+                 raster_fn=None, streams: int = 1, cams: Optional[torch.Tensor] = None,
+                 upstream_stacked: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """Forward+backward of the given views, accumulating parameter gradients into `grads`.
 
     params   : dict with contiguous fp32 CUDA tensors means3D [P,3], shs [P,M,3], opacities [P,1],
                scales [P,2], rotations [P,4] (already activated, as LaRa's renderer passes them)
     upstream : callback (view_id, color[3,H,W], allmap[8,H,W]) -> (dL_dcolor, dL_dallmap); this is
-               where the caller's loss lives (it runs on the stream the view was rendered on)
-    streams  : >1 renders the views round-robin on that many CUDA streams.  Views are independent,
-               so the latency-bound per-view kernels (preprocess, tile scan, scatter, per-tile
-               sort) and the tail of one view's blend overlap with another view's blend.  Each
-               stream accumulates into its own GradBuffer; they are summed into `grads` at the end.
-    raster_fn: test hook -- a callable pair replacing (forward_raw, backward_raw)
+               where the caller's loss lives.  Alternatively `upstream_stacked` = (dL_dcolor [V,3,H,W],
+               dL_dallmap [V,8,H,W]) when the gradients do not depend on the rendered images.
+    cams     : optional pre-packed [V,24] camera records (rasterizer.pack_cameras) of `settings_list`
+    streams  : accepted for compatibility, ignored -- all views of the call share ONE launch set
+               (every kernel carries a view dimension), which is what multi-streaming approximated
+    raster_fn: test hook -- a callable pair replacing (forward_raw, backward_raw), driven view by view
     Returns (list of (color, allmap, radii) per view, grads).
     """
     P = int(params["means3D"].shape[0])
@@ -78,50 +79,37 @@ def render_views(params: Dict[str, torch.Tensor], settings_list: Sequence[R.Gaus
     dev = params["means3D"].device
     if grads is None:
         grads = GradBuffer(P, M, dev)
-    fwd, bwd = raster_fn if raster_fn is not None else (R.forward_raw, R.backward_raw)
-    outs = []
     ids = list(view_ids) if view_ids is not None else list(range(len(settings_list)))
+    if len(ids) == 0:
+        return [], grads
 
-    def one_view(vid, rs, gbuf):
-        if raster_fn is None:
-            rs = R._check_settings(rs, dev)      # contiguous fp32 CUDA settings tensors, as the per-view path
-        color, allmap, radii, state = fwd(params["means3D"], params["shs"], None, params["opacities"],
-                                          params["scales"], params["rotations"], None, rs)
-        g_color, g_allmap = upstream(vid, color, allmap)
-        bwd(state, radii, params["means3D"], params["shs"], None, params["scales"], params["rotations"], None,
-            rs, g_color, g_allmap, out=gbuf.views, accumulate=True, need_means2D=False)
-        return color, allmap, radii
-
-    n_streams = max(1, min(int(streams), len(ids)))
-    if n_streams == 1 or not params["means3D"].is_cuda:
+    if raster_fn is not None or not params["means3D"].is_cuda:
+        fwd, bwd = raster_fn if raster_fn is not None else (R.forward_raw, R.backward_raw)
+        outs = []
         for vid, rs in zip(ids, settings_list):
-            outs.append(one_view(vid, rs, grads))
+            color, allmap, radii, state = fwd(params["means3D"], params["shs"], None, params["opacities"],
+                                              params["scales"], params["rotations"], None, rs)
+            g_color, g_allmap = upstream(vid, color, allmap)
+            bwd(state, radii, params["means3D"], params["shs"], None, params["scales"], params["rotations"], None,
+                rs, g_color, g_allmap, out=grads.views, accumulate=True, need_means2D=False)
+            outs.append((color, allmap, radii))
         return outs, grads
 
-    pool = _pool if _pool is not None else _STREAM_POOL
-    key = (dev.index, n_streams, P, M)
-    if key not in pool:
-        pool[key] = ([torch.cuda.Stream(device=dev) for _ in range(n_streams)],
-                     [GradBuffer(P, M, dev) for _ in range(n_streams - 1)])
-    side_streams, side_bufs = pool[key]
-    main = torch.cuda.current_stream(dev)
-    bufs = [grads] + list(side_bufs)
-    for b in side_bufs:
-        b.zero_()
-    for s in side_streams:
-        s.wait_stream(main)
-    for k, (vid, rs) in enumerate(zip(ids, settings_list)):
-        s = side_streams[k % n_streams]
-        with torch.cuda.stream(s):
-            o = one_view(vid, rs, bufs[k % n_streams])
-        for t in o:
-            t.record_stream(main)
-        outs.append(o)
-    for s in side_streams:
-        main.wait_stream(s)
-    for b in side_bufs:
-        grads.flat.add_(b.flat)
-    return outs, grads
-
-
-_STREAM_POOL: dict = {}
+    from .multiview import shared_view_settings
+    settings_list = [R._check_settings(rs, dev) for rs in settings_list]
+    H, W, tfx, tfy, deg, prefiltered, debug = shared_view_settings(settings_list)
+    if cams is None:
+        cams = R.pack_cameras(settings_list, dev)
+    color, allmap, radii, state = R.forward_views_raw(
+        params["means3D"], params["shs"], None, params["opacities"], params["scales"], params["rotations"], None,
+        cams, tfx, tfy, H, W, deg, prefiltered=prefiltered, debug=debug)
+    if upstream_stacked is not None:
+        g_color, g_allmap = upstream_stacked
+    else:
+        gs = [upstream(vid, color[k], allmap[k]) for k, vid in enumerate(ids)]
+        g_color = torch.stack([g[0] for g in gs]).contiguous()
+        g_allmap = torch.stack([g[1] for g in gs]).contiguous()
+    R.backward_views_raw(state, radii, params["means3D"], params["shs"], None, params["scales"], params["rotations"],
+                         None, cams, tfx, tfy, H, W, deg, g_color, g_allmap, out=grads.views, accumulate=True,
+                         need_means2D=False, debug=debug)
+    return [(color[k], allmap[k], radii[k]) for k in range(len(ids))], grads

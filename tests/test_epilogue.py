@@ -39,7 +39,7 @@ def _inputs(H, W, seed, dev="cpu"):
 @pytest.mark.skipif(not os.path.isfile(REF_RENDERER), reason="/root/reference not present (GPU box)")
 @pytest.mark.parametrize("depth_ratio", [0.0, 0.3])
 def test_torch_restatement_matches_reference_renderer_on_cpu(depth_ratio):
-    from lara_b200.epilogue import render_img_epilogue_torch
+    from oracle.torch_restatements import render_img_epilogue_torch
     spec = importlib.util.spec_from_file_location("ref_renderer_2dgs_epi", REF_RENDERER)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -65,7 +65,8 @@ def test_torch_restatement_matches_reference_renderer_on_cpu(depth_ratio):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,depth_ratio", [(64, 64, 0.0), (50, 72, 0.3), (512, 512, 0.0)])
 def test_fused_epilogue_matches_torch_ops(cuda_device, H, W, depth_ratio):
-    from lara_b200.epilogue import render_img_epilogue, render_img_epilogue_torch
+    from lara_b200.epilogue import render_img_epilogue
+    from oracle.torch_restatements import render_img_epilogue_torch
     color, allmap, rays, vm = _inputs(H, W, 1, cuda_device)
     g = torch.Generator().manual_seed(5)
     weights = {"image": torch.randn((H, W, 3), generator=g), "depth": torch.randn((H, W, 1), generator=g),
@@ -101,7 +102,8 @@ def test_fused_epilogue_feeds_rasterizer_backward(cuda_device):
     those of rasterizer -> torch epilogue."""
     import diff_surfel_rasterization as DSR
     from lara_b200 import scene as S
-    from lara_b200.epilogue import render_img_epilogue, render_img_epilogue_torch
+    from lara_b200.epilogue import render_img_epilogue
+    from oracle.torch_restatements import render_img_epilogue_torch
     dev = cuda_device
     sc = S.scene(20000, 4)
     cam = S.cameras(1, 128, 128, 0)[0]
@@ -170,7 +172,7 @@ def test_fast_renderer_matches_reference_pipeline(cuda_device, reference, fused_
     pipeline LaRa runs today), images and raw-parameter gradients."""
     import types
     from lara_b200 import scene as S
-    from lara_b200.epilogue import render_img_epilogue_torch
+    from oracle.torch_restatements import render_img_epilogue_torch
     from lara_b200.renderer import Renderer
     dev = cuda_device
     H = W = 160

@@ -3,7 +3,8 @@ import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from lara_b200.epilogue import render_img_epilogue, render_img_epilogue_torch
+from lara_b200.epilogue import render_img_epilogue
+from oracle.torch_restatements import render_img_epilogue_torch
 from test_epilogue import _inputs
 
 dev = torch.device("cuda:0")

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from lara_b200 import scene as S
-from lara_b200.epilogue import render_img_epilogue_torch
+from oracle.torch_restatements import render_img_epilogue_torch
 from lara_b200.renderer import Renderer
 import diff_surfel_rasterization as DSR
 from oracle import ref as REF
