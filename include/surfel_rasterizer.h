@@ -102,6 +102,19 @@ int srf_forward_render(srf_stream_t stream, int P, int image_height, int image_w
                        void* entries, uint32_t* point_list, void* image_state,
                        const float* background, float* out_color, float* out_others);
 
+/* ---- forward, both stages in one call (= srf_forward_preprocess followed by srf_forward_render): what
+ * rasterize_gaussians maps to when the caller sizes the binning buffers optimistically.  If the count copied to
+ * num_rendered_host exceeds `capacity`, call srf_forward_render again with larger buffers. */
+int srf_forward(srf_stream_t stream, int P, int D, int M,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* transMat_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                float tan_fovx, float tan_fovy, int image_height, int image_width, int prefiltered,
+                const float* background, size_t capacity,
+                int* radii, void* geom_state, void* tile_state, void* entries, uint32_t* point_list, void* image_state,
+                float* out_color, float* out_others, uint32_t* num_rendered_host, int raw_activations);
+
 /* ---- backward ------------------------------------------------------------------
  * Replaces Rasterizer::backward (rasterizer_impl.cu:346-448): BACKWARD::render,
  * computeAABB backward, BACKWARD::preprocess.  Consumes the state the forward left in
@@ -221,6 +234,20 @@ int srf_loss_backward(srf_stream_t stream, int V, int image_height, int image_wi
                       const float* image, const float* target_hwc, const float* rend_normal, const float* depth_normal,
                       const float* acc_map, const float* upstream,
                       float* g_image, float* g_rend_normal, float* g_depth_normal, float* g_rend_dist);
+
+/* ---- decoder epilogue: MLP output -> Gaussian-parameter tensors (next-row: lightning/network.py:261-278,425-429) ----
+ * `params` is the decoder MLP's fp32 output [B, N, K*C], C = 10 + sh_dim, each row = offset[3] | sh[sh_dim] |
+ * opacity[1] | scaling[2] | rotation[4].  Writes the five CONTIGUOUS tensors the rasterizer consumes, for all B*N*K
+ * Gaussians in [b][n][k] order:  centers = group_centers[n] + (sigmoid(offset)*2 - 1) * half_cell_size,
+ * shs (row copy), opacity + opacity_shift, scaling + scaling_shift, rotation (row copy).  The backward takes the
+ * five gradients (NULL = zero) and writes g_params [B,N,K*C] (sigmoid vjp applied).                          */
+int srf_decoder_layout_forward(srf_stream_t stream, size_t B, int N, int K, int sh_dim,
+                               float opacity_shift, float scaling_shift, float half_cell_size,
+                               const float* params, const float* group_centers,
+                               float* centers, float* shs, float* opacity, float* scaling, float* rotation);
+int srf_decoder_layout_backward(srf_stream_t stream, size_t B, int N, int K, int sh_dim, float half_cell_size,
+                                const float* params, const float* g_centers, const float* g_shs, const float* g_opacity,
+                                const float* g_scaling, const float* g_rotation, float* g_params);
 
 /* ---- optional per-kernel timing (no reference counterpart; used by bench.py's roofline) --
  * Between srf_profile_begin() and srf_profile_end() every kernel launch made by this

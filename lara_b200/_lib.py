@@ -45,6 +45,19 @@ SIGNATURES = {
         _P, _P, _P,                         # entries, point_list, image_state
         _P, _P, _P,                         # background, out_color, out_others
     ]),
+    "srf_forward": (c_int, [
+        _P, c_int, c_int, c_int,            # stream, P, D, M
+        _P, _P, _P,                         # means3D, shs, colors_precomp
+        _P, _P, c_float,                    # opacities, scales, scale_modifier
+        _P, _P,                             # rotations, transMat_precomp
+        _P, _P, _P,                         # viewmatrix, projmatrix, campos
+        c_float, c_float, c_int, c_int,     # tan_fovx, tan_fovy, H, W
+        c_int,                              # prefiltered
+        _P, c_size_t,                       # background, capacity
+        _P, _P, _P, _P, _P, _P,             # radii, geom_state, tile_state, entries, point_list, image_state
+        _P, _P, _P,                         # out_color, out_others, num_rendered_host
+        c_int,                              # raw_activations
+    ]),
     "srf_backward": (c_int, [
         _P, c_int, c_int, c_int, c_int, c_int,   # stream, P, D, M, H, W
         c_size_t, _P,                            # capacity, background
@@ -94,6 +107,8 @@ SIGNATURES = {
     "srf_views_epilogue_backward": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srf_loss_forward": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "srf_loss_backward": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srf_decoder_layout_forward": (c_int, [_P, c_size_t, c_int, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "srf_decoder_layout_backward": (c_int, [_P, c_size_t, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "srf_mark_visible": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "srf_epilogue_forward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srf_epilogue_backward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -116,7 +116,7 @@ int bwd_variant() {
     static const int v = [] {
         const char* e = getenv("SRF_BWD_VARIANT");
         const int x = e ? atoi(e) : 2;
-        return (x >= 1 && x <= 3) ? x : 2;
+        return (x >= 1 && x <= 5) ? x : 2;
     }();
     return v;
 }
@@ -491,6 +491,24 @@ int srf_backward(srf_stream_t stream_, int P, int D, int M, int image_height, in
                          dL_dopacity, dL_dscales, dL_drotations, dL_dtransMat, raw_activations);
 }
 
+// both forward stages in one call (one host->library transition per view in the drop-in path)
+int srf_forward(srf_stream_t stream_, int P, int D, int M,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* transMat_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                float tan_fovx, float tan_fovy, int image_height, int image_width, int prefiltered,
+                const float* background, size_t capacity,
+                int* radii, void* geom_state, void* tile_state, void* entries, uint32_t* point_list, void* image_state,
+                float* out_color, float* out_others, uint32_t* num_rendered_host, int raw_activations) {
+    int rc = srf_forward_preprocess(stream_, P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+                                    transMat_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, image_height,
+                                    image_width, prefiltered, radii, geom_state, tile_state, num_rendered_host, raw_activations);
+    if (rc != 0) return rc;
+    return srf_forward_render(stream_, P, image_height, image_width, capacity, geom_state, tile_state, entries, point_list,
+                              image_state, background, out_color, out_others);
+}
+
 // ---- all V target views of one scene in one launch set (reference caller loop: lightning/network.py:484-497)
 int srf_views_workspace_bytes(int V, int P, int H, int W, size_t capacity, size_t bytes[6]) {
     if (V <= 0 || P < 0 || H <= 0 || W <= 0 || !bytes) return fail("srf_views_workspace_bytes: bad arguments");
@@ -661,6 +679,44 @@ int srf_loss_backward(srf_stream_t stream_, int V, int image_height, int image_w
     a.g_image = g_image; a.g_rend_normal = g_rend_normal; a.g_depth_normal = g_depth_normal; a.g_dist = g_rend_dist;
     cudaError_t e = srf::launch_loss_fused(a, static_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return cuda_fail("loss_grads launch", e);
+    return 0;
+}
+
+int srf_decoder_layout_forward(srf_stream_t stream_, size_t B, int N, int K, int sh_dim,
+                               float opacity_shift, float scaling_shift, float half_cell_size,
+                               const float* params, const float* group_centers,
+                               float* centers, float* shs, float* opacity, float* scaling, float* rotation) {
+    if (N <= 0 || K <= 0 || sh_dim < 3 || sh_dim % 3 != 0) return fail("srf_decoder_layout_forward: bad sizes");
+    if (!params || !group_centers || !centers || !shs || !opacity || !scaling || !rotation)
+        return fail("srf_decoder_layout_forward: null pointer");
+    if ((reinterpret_cast<uintptr_t>(rotation) & 15) || (reinterpret_cast<uintptr_t>(scaling) & 7) ||
+        ((sh_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15)))
+        return fail("srf_decoder_layout_forward: outputs must be 16-byte aligned");
+    srf::DecoderArgs a;
+    memset(&a, 0, sizeof(a));
+    a.total = B * (size_t)N * (size_t)K; a.N = N; a.K = K; a.C = 10 + sh_dim; a.sh_dim = sh_dim;
+    a.opacity_shift = opacity_shift; a.scaling_shift = scaling_shift; a.half_cell = half_cell_size;
+    a.params = params; a.group_centers = group_centers;
+    a.centers = centers; a.shs = shs; a.opacity = opacity; a.scaling = scaling; a.rotation = rotation;
+    cudaError_t e = srf::launch_decoder_layout(a, false, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("decoder_layout launch", e);
+    return 0;
+}
+
+int srf_decoder_layout_backward(srf_stream_t stream_, size_t B, int N, int K, int sh_dim, float half_cell_size,
+                                const float* params, const float* g_centers, const float* g_shs, const float* g_opacity,
+                                const float* g_scaling, const float* g_rotation, float* g_params) {
+    if (N <= 0 || K <= 0 || sh_dim < 3 || sh_dim % 3 != 0) return fail("srf_decoder_layout_backward: bad sizes");
+    if (!params || !g_params) return fail("srf_decoder_layout_backward: null pointer");
+    srf::DecoderArgs a;
+    memset(&a, 0, sizeof(a));
+    a.total = B * (size_t)N * (size_t)K; a.N = N; a.K = K; a.C = 10 + sh_dim; a.sh_dim = sh_dim;
+    a.half_cell = half_cell_size;
+    a.params = params;
+    a.g_centers = g_centers; a.g_shs = g_shs; a.g_opacity = g_opacity; a.g_scaling = g_scaling; a.g_rotation = g_rotation;
+    a.g_params = g_params;
+    cudaError_t e = srf::launch_decoder_layout(a, true, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("decoder_layout backward launch", e);
     return 0;
 }
 

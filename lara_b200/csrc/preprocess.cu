@@ -285,21 +285,27 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessArgs a) {
                 const float qw = tau * (Twx * Twx + Twy * Twy) - Twz * Twz;
                 if (qw < 0.0f) {
                     const float iq = 1.0f / qw;
-                    // rows whose projective extent we need: Tu, Tv, Tu+Tv, Tu-Tv; disc radius along each
-                    const float rx[4] = {Tux, Tvx, Tux + Tvx, Tux - Tvx};
-                    const float ry[4] = {Tuy, Tvy, Tuy + Tvy, Tuy - Tvy};
-                    const float rz[4] = {Tuz, Tvz, Tuz + Tvz, Tuz - Tvz};
+                    // rows whose projective extent we need: Tu, Tv, Tu+Tv, Tu-Tv, TRANSLATED so that the splat's screen
+                    // centre is the origin (row - centre * Tw).  Evaluated in absolute pixel coordinates the extent
+                    // h^2 = c^2 - (...) cancels catastrophically: c^2 ~ 1e6 at 1024^2 has an fp32 spacing of 0.125,
+                    // as large as h^2 itself for small low-opacity splats (measured: 2 wrongly culled pairs per
+                    // 262144-splat 1024^2 view).  Around the centre every term is O(h^2).
                     const float dc[4] = {cxs, cys, cxs + cys, cxs - cys};
+                    const float ax[4] = {Tux, Tvx, Tux + Tvx, Tux - Tvx};
+                    const float ay[4] = {Tuy, Tvy, Tuy + Tvy, Tuy - Tvy};
+                    const float az[4] = {Tuz, Tvz, Tuz + Tvz, Tuz - Tvz};
                     const float dr[4] = {r2, r2, 1.41421357f * r2, 1.41421357f * r2};
                     const float mg[4] = {0.0625f, 0.0625f, 0.0884f, 0.0884f};   // 1/16 px (x sqrt2 along the diagonals): the masks are per pixel now
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float c = (tau * (rx[k] * Twx + ry[k] * Twy) - rz[k] * Twz) * iq;
-                        const float h = sqrtf(fmaxf(0.0f, c * c - (tau * (rx[k] * rx[k] + ry[k] * ry[k]) - rz[k] * rz[k]) * iq));
-                        float l0 = fminf(dc[k] - dr[k], c - h), h0 = fmaxf(dc[k] + dr[k], c + h);
-                        const float m = mg[k] + 1.0e-3f * (h0 - l0);
-                        lo[k] = l0 - m - dc[k];      // offsets from the centre (x, y, x+y, x-y of it)
-                        hi[k] = h0 + m - dc[k];
+                        const float rx = fmaf(-dc[k], Twx, ax[k]), ry = fmaf(-dc[k], Twy, ay[k]), rz = fmaf(-dc[k], Twz, az[k]);
+                        const float c = (tau * (rx * Twx + ry * Twy) - rz * Twz) * iq;          // offset of the ellipse centre from (cxs, cys)
+                        const float h = sqrtf(fmaxf(0.0f, c * c - (tau * (rx * rx + ry * ry) - rz * rz) * iq));
+                        const float l0 = fminf(-dr[k], c - h), h0 = fmaxf(dr[k], c + h);
+                        // margin: 1/16 px + 0.1 % of the width + the rounding of the translated rows (|row| * 2^-22 / |Tw.z|)
+                        const float m = mg[k] + 1.0e-3f * (h0 - l0) + 4.0e-7f * (fabsf(az[k]) + fabsf(dc[k] * Twz)) * fabsf(Twz * iq);
+                        lo[k] = l0 - m;      // offsets from the centre (x, y, x+y, x-y of it)
+                        hi[k] = h0 + m;
                     }
                 } else {
                     for (int k = 0; k < 4; ++k) { lo[k] = -3.0e38f; hi[k] = 3.0e38f; }   // tau-ellipse crosses the camera plane: unbounded

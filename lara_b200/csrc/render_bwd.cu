@@ -38,11 +38,6 @@ __device__ __forceinline__ float rcp_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float ex2_fast(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -52,38 +47,57 @@ __device__ __forceinline__ f32x2 shfl_xor2(f32x2 v, int m) {
     return (f32x2)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
 }
 
-// Pair evaluation of the backward (same quantities as eval_pair(), forward.cu:353-398).  The backward only
-// has to agree with the forward's accept/reject decisions up to measure-zero ties and needs its values to
-// ~1e-6, so the two IEEE divisions and expf() of the forward-deciding chain become MUFU.RCP / MUFU.EX2
-// (<= 2 ulp).  A pair whose alpha sits within an ulp of 1/255 may be taken differently from the forward:
-// its weight is < 0.4 % of one pixel.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Pair evaluation of phase 1.  What must agree with the forward BIT FOR BIT are the accept / reject decisions
+// (a pair taken by one pass and not by the other shifts the whole transmittance chain of its pixel); the values
+// only need ~1e-6.  So the two IEEE divisions and expf() of eval_pair() become MUFU.RCP / MUFU.EX2 (<= 2 ulp), and a
+// pair that lands within a 1e-5 relative band of a decision threshold (alpha = 1/255, depth = 0.2) -- one in ~1e5 --
+// is re-evaluated with the forward's exact sequence.  k, l and p = k x l are the forward's own operations, so the
+// p.z != 0 test is exact as is.
 struct PairBwd {
-    float sx, sy, depth, G, alpha;
+    float depth, G, alpha;
     bool lowpass, valid;
 };
+template <bool EXACT>
 __device__ __forceinline__ void eval_pair_bwd(const float4 q0, const float4 q1, const float4 q2, const float pixx,
-                                              const float pixy, PairBwd& e) {
+                                              const float pixy, PairBwd& r) {
+    if (EXACT) {
+        PairEval e;
+        eval_pair(q0, q1, q2, pixx, pixy, e);
+        r.depth = e.depth; r.G = e.G; r.alpha = e.alpha; r.lowpass = !(e.rho3d <= e.rho2d); r.valid = e.valid;
+        return;
+    }
     const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
     const f32x2 pix2 = pk2(pixx, pixy);
     const float2 klx = up2(fma2(pix2, bc2(Twx), pk2(-q0.x, -q0.y)));
     const float2 kly = up2(fma2(pix2, bc2(Twy), pk2(-q0.z, -q0.w)));
     const float2 klz = up2(fma2(pix2, bc2(Twz), pk2(-q1.x, -q1.y)));
-    const float pz = fmaf(klx.x, kly.y, -(kly.x * klx.y));
-    const float px = fmaf(kly.x, klz.y, -(klz.x * kly.y));
-    const float py = fmaf(klz.x, klx.y, -(klx.x * klz.y));
+    const float pz = fma_(klx.x, kly.y, -fmul_(kly.x, klx.y));
+    const float px = fma_(kly.x, klz.y, -fmul_(klz.x, kly.y));
+    const float py = fma_(klz.x, klx.y, -fmul_(klx.x, klz.y));
     const float rpz = rcp_fast(pz);
-    e.sx = px * rpz; e.sy = py * rpz;
-    const float rho3d = fmaf(e.sx, e.sx, e.sy * e.sy);
+    const float sx = px * rpz, sy = py * rpz;
+    const float rho3d = fmaf(sx, sx, sy * sy);
     const float2 d = up2(sub2(pk2(q2.y, q2.z), pix2));
     const float rho2d = 2.0f * fmaf(d.x, d.x, d.y * d.y);
-    e.lowpass = !(rho3d <= rho2d);
+    r.lowpass = !(rho3d <= rho2d);
     const float rho = fminf(rho3d, rho2d);
-    const float depth3d = Twz + fmaf(Twx, e.sx, Twy * e.sy);
-    e.depth = e.lowpass ? Twz : depth3d;
-    // exp(-rho/2) = 2^(-rho * log2(e)/2)
-    e.G = ex2_fast(rho * -0.72134752044448170f);
-    e.alpha = fminf(0.99f, q2.w * e.G);
-    e.valid = (pz != 0.0f) && !(e.depth < SRF_NEAR_F) && !(rho < 0.0f) && !(e.alpha < 0.00392156862745098f);
+    r.depth = r.lowpass ? Twz : Twz + fmaf(Twx, sx, Twy * sy);
+    r.G = ex2_fast(rho * -0.72134752044448170f);          // exp(-rho/2)
+    const float araw = q2.w * r.G;
+    r.alpha = fminf(0.99f, araw);
+    r.valid = (pz != 0.0f) && !(r.depth < SRF_NEAR_F) && !(araw < 0.00392156862745098f);
+    const bool near_thr = fabsf(araw - 0.00392156862745098f) < 4.0e-8f || fabsf(r.depth - SRF_NEAR_F) < 2.0e-6f;
+    if (near_thr && pz != 0.0f) {
+        PairEval e;
+        eval_pair(q0, q1, q2, pixx, pixy, e);
+        r.depth = e.depth; r.G = e.G; r.alpha = e.alpha; r.lowpass = !(e.rho3d <= e.rho2d); r.valid = e.valid;
+    }
 }
 
 template <int BATCH>
@@ -91,20 +105,23 @@ struct BwdSmem {
     static constexpr size_t rec = 0;                                                         // float4 [6][BATCH]
     static constexpr size_t x = rec + sizeof(float4) * SRF_REC_QUADS * BATCH;                // float [warps][3][16][32]
     static constexpr size_t pixA = x + sizeof(float) * SRF_CTA_WARPS * 3 * kBwdGroup * 32;   // float4 [256] dn0 dn1 dn2 dpix0
-    static constexpr size_t pixB = pixA + sizeof(float4) * SRF_CTA_THREADS;                  // float2 [256] dpix1 dpix2
-    static constexpr size_t list = pixB + sizeof(float2) * SRF_CTA_THREADS;                  // uint8 [warps][BATCH]
+    static constexpr size_t pixB = pixA + sizeof(float4) * SRF_CTA_THREADS;                  // float4 [256] dpix1 dpix2 dL_ddepth dL_dalpha
+    static constexpr size_t list = pixB + sizeof(float4) * SRF_CTA_THREADS;                  // uint8 [warps][BATCH]
     static constexpr size_t wmax = list + (size_t)SRF_CTA_WARPS * BATCH;                     // int [warps]
     static constexpr size_t total = wmax + sizeof(int) * SRF_CTA_WARPS;
 };
 
-template <int BATCH, int MINB>
+// EXACT : phase 1 evaluates pairs with the forward's exact sequence (else approximate + exact re-check at thresholds)
+// P2WALK: every phase-2 lane walks its own contributing pixels (else all lanes step through the 16 pixels together)
+// SMEMC : phase 1 reads the pixel's upstream gradients from shared memory (eight registers less)
+template <int BATCH, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
 __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(RenderBwdArgs a) {
     static_assert(BATCH <= 256, "hit lists are uint8");
     extern __shared__ __align__(16) unsigned char smem[];
     typedef BwdSmem<BATCH> L;
     float4 (*s_rec)[BATCH] = reinterpret_cast<float4 (*)[BATCH]>(smem + L::rec);
     float4* s_pixA = reinterpret_cast<float4*>(smem + L::pixA);
-    float2* s_pixB = reinterpret_cast<float2*>(smem + L::pixB);
+    float4* s_pixB = reinterpret_cast<float4*>(smem + L::pixB);
     int* s_wmax = reinterpret_cast<int*>(smem + L::wmax);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -130,9 +147,10 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
     tile_pixel(tid, lx, ly);
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
-    const float pixx = (float)pxi + 0.5f, pixy = (float)pyi + 0.5f;
     const size_t pix = (size_t)pyi * a.W + pxi;
-    const WarpRect wrect = make_warp_rect(txi, tyi, wid);
+    // first pixel centre of this warp's 8x4 block; the block's bounds are rebuilt from it where needed
+    // (two live registers instead of eight)
+    const float bx0 = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, by0 = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f;
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
     const float bg_dot_dpixel = __ldg(a.bg + 0) * dpix0 + __ldg(a.bg + 1) * dpix1 + __ldg(a.bg + 2) * dpix2;
     // the upstream values phase 2 multiplies w with, indexed by the pixel's thread id (= wid*32 + lane)
     s_pixA[tid] = make_float4(dn0, dn1, dn2, dpix0);
-    s_pixB[tid] = make_float2(dpix1, dpix2);
+    s_pixB[tid] = make_float4(dpix1, dpix2, dL_ddepth, dL_daccum);
 
     // deepest list entry any pixel of the warp / of the tile blended
     int wmax = last_contributor;
@@ -177,11 +195,11 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
 
     // accum_rec / last_* recursions of backward.cu:331-385, two channels per packed fp32x2 register:
     // (c0,c1) (c2,depth) (n0,n1) (n2,alpha); the matching upstream gradients are paired the same way
+    // (the reference keeps the previous splat in last_* and folds it in at the top of the next iteration;
+    //  folding it in at the bottom of its own iteration is the same arithmetic and needs no such state)
     f32x2 acc_c01 = 0ull, acc_c2d = 0ull, acc_n01 = 0ull, acc_n2a = 0ull;
-    f32x2 last_c01 = 0ull, last_c2d = 0ull, last_n01 = 0ull, last_n2a = 0ull;
-    float last_alpha = 0.f;
-    const f32x2 dpix01 = pk2(dpix0, dpix1), dpix2d = pk2(dpix2, dL_ddepth);
-    const f32x2 dn01 = pk2(dn0, dn1), dn2a = pk2(dn2, dL_daccum);
+    const f32x2 r_dpix01 = pk2(dpix0, dpix1), r_dpix2d = pk2(dpix2, dL_ddepth);
+    const f32x2 r_dn01 = pk2(dn0, dn1), r_dn2a = pk2(dn2, dL_daccum);
     float last_dL_dT = 0.f;
     const float nTfinal_bg = -T_final * bg_dot_dpixel;
 
@@ -211,7 +229,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
         for (int c = 0; c < cnt; c += 32) {
             const int jt = c + lane;
             bool hit = false;
-            if (jt < cnt && n_eff - 1 - (b * BATCH + jt) < wmax) hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
+            if (jt < cnt && n_eff - 1 - (b * BATCH + jt) < wmax) hit = octagon_hits(s_rec[2][jt], s_rec[5][jt], warp_rect_at(bx0, by0));
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
             if (hit) s_listw[nh + __popc(hits & ((1u << lane) - 1u))] = (uint8_t)jt;
             nh += __popc(hits);
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                 uint32_t m = 0;
                 if (g0 + lane < nh) {
                     const int j = s_listw[g0 + lane];
-                    m = octagon_pixel_mask(s_rec[2][j], s_rec[5][j], wrect);
+                    m = octagon_pixel_mask(s_rec[2][j], s_rec[5][j], warp_rect_at(bx0, by0));
                 }
                 colword = transpose32(m, lane);
             }
@@ -240,7 +258,8 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                 uint32_t bits = (colword >> (sub * kBwdGroup)) & 0xffffu;
                 if (last_contributor == 0) bits = 0;
                 uint32_t vbits = 0;
-                while (__any_sync(0xffffffffu, bits != 0)) {
+                const int iters1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(bits));
+                for (int it = 0; it < iters1; ++it) {
                     if (bits == 0) continue;
                     const int i = __ffs(bits) - 1;
                     bits &= bits - 1;
@@ -248,8 +267,9 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                     const int pos = n_eff - 1 - (b * BATCH + j);   // 0-based position in the tile list
                     if (pos >= last_contributor) continue;
                     PairBwd e;
-                    eval_pair_bwd(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
+                    eval_pair_bwd<EXACT>(s_rec[0][j], s_rec[1][j], s_rec[2][j], bx0 + (float)(lane & 7), by0 + (float)(lane >> 3), e);
                     if (!e.valid) continue;
+                    const bool lowpass = e.lowpass;
                     const float4 q3 = s_rec[3][j];
                     const float4 q4 = s_rec[4][j];
                     const float alpha = e.alpha, c_d = e.depth;
@@ -258,22 +278,27 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                     const float r1ma = rcp_fast(1.0f - alpha);   // 1 - alpha >= 0.01
                     T = T * r1ma;
                     const float w = alpha * T;
-                    // accum_rec <- last_alpha * last + (1 - last_alpha) * accum_rec  (all eight channels)
-                    const f32x2 la2 = bc2(last_alpha), oma2 = bc2(1.0f - last_alpha);
-                    acc_c01 = fma2(last_c01, la2, mul2(acc_c01, oma2));
-                    acc_c2d = fma2(last_c2d, la2, mul2(acc_c2d, oma2));
-                    acc_n01 = fma2(last_n01, la2, mul2(acc_n01, oma2));
-                    acc_n2a = fma2(last_n2a, la2, mul2(acc_n2a, oma2));
-                    last_c01 = pk2(q4.x, q4.y); last_c2d = pk2(q4.z, c_d);
-                    last_n01 = pk2(q3.x, q3.y); last_n2a = pk2(q3.z, 1.0f);
+                    const f32x2 cur_c01 = pk2(q4.x, q4.y), cur_c2d = pk2(q4.z, c_d);
+                    const f32x2 cur_n01 = pk2(q3.x, q3.y), cur_n2a = pk2(q3.z, 1.0f);
                     // dL_dalpha += (channel - accum_rec) * dL_dchannel over colour, depth, normal, alpha
-                    f32x2 dsum = mul2(sub2(last_c01, acc_c01), dpix01);
-                    dsum = fma2(sub2(last_c2d, acc_c2d), dpix2d, dsum);
-                    dsum = fma2(sub2(last_n01, acc_n01), dn01, dsum);
-                    dsum = fma2(sub2(last_n2a, acc_n2a), dn2a, dsum);
+                    f32x2 dpix01 = r_dpix01, dpix2d = r_dpix2d, dn01 = r_dn01, dn2a = r_dn2a;
+                    if (SMEMC) {
+                        const float4 ua = s_pixA[tid], ub = s_pixB[tid];
+                        dpix01 = pk2(ua.w, ub.x); dpix2d = pk2(ub.y, ub.z); dn01 = pk2(ua.x, ua.y); dn2a = pk2(ua.z, ub.w);
+                    }
+                    f32x2 dsum = mul2(sub2(cur_c01, acc_c01), dpix01);
+                    dsum = fma2(sub2(cur_c2d, acc_c2d), dpix2d, dsum);
+                    dsum = fma2(sub2(cur_n01, acc_n01), dn01, dsum);
+                    dsum = fma2(sub2(cur_n2a, acc_n2a), dn2a, dsum);
                     const float2 dsum_ = up2(dsum);
+                    // accum_rec <- alpha * channel + (1 - alpha) * accum_rec  (all eight channels), for the next splat
+                    const f32x2 la2 = bc2(alpha), oma2 = bc2(1.0f - alpha);
+                    acc_c01 = fma2(cur_c01, la2, mul2(acc_c01, oma2));
+                    acc_c2d = fma2(cur_c2d, la2, mul2(acc_c2d, oma2));
+                    acc_n01 = fma2(cur_n01, la2, mul2(acc_n01, oma2));
+                    acc_n2a = fma2(cur_n2a, la2, mul2(acc_n2a, oma2));
 
-                    float dL_dz = w * dL_ddepth, dL_dweight = 0.0f;
+                    float dL_dz = w * up2(dpix2d).y, dL_dweight = 0.0f;
                     // distortion / median terms (backward.cu:350-368).  m_d = (FAR d - FAR NEAR)/((FAR-NEAR) d)
                     // = c1 - c2/d and d m_d/dd = c2/d^2; the reference evaluates both in double.  fp32 is
                     // enough here: the weight term below is stationary in m_d (its derivative is
@@ -291,13 +316,12 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                     const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
                     dL_dz += dL_dmd * dmd_dd;
                     dL_dalpha *= T;
-                    last_alpha = alpha;
                     // background term (backward.cu:391-396)
                     dL_dalpha = fmaf(nTfinal_bg, r1ma, dL_dalpha);
 
                     // park the three scalars phase 2 needs; the sign of w carries the branch (w > 0 always)
                     float* xp = s_xw + (i * 32 + (lane ^ i));
-                    xp[0] = e.lowpass ? -w : w;
+                    xp[0] = lowpass ? -w : w;
                     xp[kBwdGroup * 32] = e.G * dL_dalpha;
                     xp[2 * kBwdGroup * 32] = dL_dz;
                     vbits |= 1u << i;
@@ -310,9 +334,10 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                 const uint32_t tw = transpose32(vbits, lane);
                 const uint32_t word = __shfl_sync(0xffffffffu, tw, p2_i);
                 const bool have = gbase + p2_i < nh;
-                const uint32_t mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
+                uint32_t mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
                 uint32_t tmask = __reduce_or_sync(0xffffffffu, mybits);
-                if (tmask == 0) continue;
+                const int iters2 = P2WALK ? (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(mybits)) : __popc(tmask);
+                if (iters2 == 0) continue;
                 const int j2 = have ? (int)lst[p2_i] : 0;
                 const float4 q0 = s_rec[0][j2], q1 = s_rec[1][j2], q2 = s_rec[2][j2];
                 const uint32_t splat_id = __float_as_uint(s_rec[4][j2].w);
@@ -324,18 +349,25 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                 // (DN0,DN1) (DN2,DC0) (DC1,DC2) (DM0,DM1)
                 f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull, A3 = 0ull, A4 = 0ull, A5 = 0ull, A6 = 0ull, A7 = 0ull, A8 = 0ull;
                 const float* xrow = s_xw + p2_i * 32;
-                const float ybase = wrect.ymin + (float)(2 * p2_h);
+                const float ybase = by0 + (float)(2 * p2_h);
                 const int pbase = wid * 32 + 16 * p2_h;
-                while (tmask) {
-                    const int t = __ffs(tmask) - 1;
-                    tmask &= tmask - 1;
-                    if (!((mybits >> t) & 1u)) continue;
+                for (int it = 0; it < iters2; ++it) {
+                    int t;
+                    if (P2WALK) {
+                        if (mybits == 0) continue;
+                        t = __ffs(mybits) - 1;             // every lane walks its own contributing pixels
+                        mybits &= mybits - 1;
+                    } else {
+                        t = __ffs(tmask) - 1;              // all lanes step through the half block's pixels together
+                        tmask &= tmask - 1;
+                        if (!((mybits >> t) & 1u)) continue;
+                    }
                     const int p = t + 16 * p2_h;
-                    const float ppx = wrect.xmin + (float)(t & 7), ppy = ybase + (float)(t >> 3);
+                    const float ppx = bx0 + (float)(t & 7), ppy = ybase + (float)(t >> 3);
                     const float* xp = xrow + (p ^ p2_i);
                     const float ws = xp[0], GdA = xp[kBwdGroup * 32], dL_dz = xp[2 * kBwdGroup * 32];
                     const float4 pa = s_pixA[pbase + t];
-                    const float2 pb = s_pixB[pbase + t];
+                    const float4 pb = s_pixB[pbase + t];
                     const float w = fabsf(ws);
                     const f32x2 w2 = bc2(w);
                     fma2_acc(A5, w2, pk2(pa.x, pa.y));      // dL/dnormal
@@ -408,6 +440,16 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
 
 cudaError_t launch_render_bwd_v1(const RenderBwdArgs& a, cudaStream_t stream);
 
+template <int B, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
+static cudaError_t launch_variant(const RenderBwdArgs& a, dim3 grid, cudaStream_t stream) {
+    auto k = render_bwd_kernel<B, MINB, EXACT, P2WALK, SMEMC>;
+    // the opt-in is per device (and cheap): made on every call for the current device
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
+    if (e != cudaSuccess) return e;
+    k<<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
+    return cudaSuccess;
+}
+
 cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     const int ntiles = a.gx * a.gy;
     if (ntiles <= 0 || a.nviews <= 0) return cudaSuccess;
@@ -416,14 +458,11 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     prof_start(K_RENDER_BWD, stream);
     cudaError_t e = cudaSuccess;
     const dim3 grid(ntiles, a.nviews);
-    if (variant == 3) {
-        constexpr int B = 128;
-        e = cudaFuncSetAttribute(render_bwd_kernel<B, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
-        if (e == cudaSuccess) render_bwd_kernel<B, 3><<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
-    } else {
-        constexpr int B = 256;
-        e = cudaFuncSetAttribute(render_bwd_kernel<B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
-        if (e == cudaSuccess) render_bwd_kernel<B, 2><<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
+    switch (variant) {
+        case 3: e = launch_variant<160, 3, false, true, true>(a, grid, stream); break;
+        case 4: e = launch_variant<256, 2, false, false, false>(a, grid, stream); break;
+        case 5: e = launch_variant<256, 2, true, true, false>(a, grid, stream); break;
+        default: e = launch_variant<256, 2, false, true, false>(a, grid, stream); break;
     }
     prof_stop(K_RENDER_BWD, stream);
     return e != cudaSuccess ? e : cudaGetLastError();

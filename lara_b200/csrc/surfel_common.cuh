@@ -169,6 +169,15 @@ __device__ __forceinline__ WarpRect make_warp_rect(int tile_x, int tile_y, int w
     w.vmin = w.xmin - w.ymax; w.vmax = w.xmax - w.ymin;
     return w;
 }
+// the same rectangle from the block's first pixel centre
+__device__ __forceinline__ WarpRect warp_rect_at(float xmin, float ymin) {
+    WarpRect w;
+    w.xmin = xmin; w.xmax = xmin + 7.0f;
+    w.ymin = ymin; w.ymax = ymin + 3.0f;
+    w.umin = w.xmin + w.ymin; w.umax = w.xmax + w.ymax;
+    w.vmin = w.xmin - w.ymax; w.vmax = w.xmax - w.ymin;
+    return w;
+}
 // true if the splat's conservative octagon (q5, centred at q2.yz) may touch the warp's block
 __device__ __forceinline__ bool octagon_hits(const float4 q2, const float4 q5, const WarpRect& w) {
     const float cx = q2.y, cy = q2.z;

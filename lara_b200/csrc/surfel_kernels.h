@@ -174,6 +174,20 @@ struct LossArgs {
 };
 cudaError_t launch_loss_fused(const LossArgs& a, cudaStream_t stream);
 
+// Decoder epilogue (lightning/network.py:261-278, 425-429): MLP output rows -> the five
+// contiguous parameter tensors, and the mirror-image backward.
+struct DecoderArgs {
+    size_t total;                // B * N * K Gaussians
+    int N, K, C, sh_dim;         // voxels per scene, Gaussians per voxel, floats per row (10 + sh_dim), SH floats
+    float opacity_shift, scaling_shift, half_cell;
+    const float* params;         // [B,N,K*C] MLP output (fp32)
+    const float* group_centers;  // [N,3]
+    float* centers; float* shs; float* opacity; float* scaling; float* rotation;     // forward outputs
+    const float* g_centers; const float* g_shs; const float* g_opacity; const float* g_scaling; const float* g_rotation;
+    float* g_params;             // [B,N,K*C] backward output
+};
+cudaError_t launch_decoder_layout(const DecoderArgs& a, bool backward, cudaStream_t stream);
+
 // Optional per-kernel CUDA-event timing (srf_profile_begin/end in the C ABI); no-ops unless enabled.
 enum KernelId { K_PREPROCESS_FWD = 0, K_TILE_SCAN, K_SCATTER, K_SORT_SMALL, K_SORT_BIG, K_RENDER_FWD,
                 K_RENDER_BWD, K_PREPROCESS_BWD, K_COUNT };
@@ -181,7 +195,7 @@ void prof_start(int kernel, cudaStream_t stream);
 void prof_stop(int kernel, cudaStream_t stream);
 
 // runtime A/B switches (environment, read once): SRF_BWD_VARIANT = 1 (round-1 reduce-scatter kernel),
-// 2 (two-phase, 256-splat rounds, default), 3 (two-phase, 128-splat rounds)
+// 2 (two-phase, 256-splat rounds, default), 3 (two-phase, 160-splat rounds, 3 CTAs/SM)
 int bwd_variant();
 // number of SMs of the current device (cached per device)
 int sm_count();

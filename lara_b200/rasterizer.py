@@ -258,17 +258,22 @@ class ForwardState:
         return c[0] if self.nviews == 1 else list(c)
 
 
-def _launch_forward(device, lib, nviews, P, capacity, debug, call_pre, call_render, state_blobs, alloc_binning):
+def _launch_forward(device, lib, nviews, P, capacity, debug, call_pre, call_render, state_blobs, alloc_binning,
+                    call_both=None):
     """Common enqueue sequence of the per-view and the batched forward:
-    stage 1 (preprocess + tile scan + async count read-back) -> event -> stage 2 with an optimistic capacity."""
+    stage 1 (preprocess + tile scan + async count read-back) and stage 2 (binning + blend) with an optimistic
+    capacity, then an event for whoever eventually asks for the instance counts."""
     _drain_ready(device)
     rb = _take_readback(device, nviews)
     slot, ev = rb
-    call_pre(slot.data_ptr())
-    ev.record()
     geom, tile, image = state_blobs
     entries, point_list = alloc_binning(capacity)
-    call_render(capacity, entries, point_list)
+    if call_both is not None:
+        call_both(slot.data_ptr(), capacity, entries, point_list)
+    else:
+        call_pre(slot.data_ptr())
+        call_render(capacity, entries, point_list)
+    ev.record()
     state = ForwardState(geom, tile, image, point_list, capacity, nviews=nviews)
 
     def rerun(new_capacity: int):
@@ -331,16 +336,17 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
     projm = raster_settings.projmatrix
     campos = raster_settings.campos
 
-    def call_pre(slot_ptr):
-        _lib.check(lib.srf_forward_preprocess(
+    def call_both(slot_ptr, capacity, entries, point_list):
+        _lib.check(lib.srf_forward(
             sptr, P, int(raster_settings.sh_degree), M,
             _ptr(means3D), _ptr(shs), _ptr(colors_precomp),
             _ptr(opacities), _ptr(scales), float(raster_settings.scale_modifier),
             _ptr(rotations), _ptr(transMat_precomp),
             _ptr(viewm), _ptr(projm), _ptr(campos),
             float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
-            1 if raster_settings.prefiltered else 0,
-            radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), slot_ptr, 1 if raw_activations else 0), lib)
+            1 if raster_settings.prefiltered else 0, _ptr(bg), capacity,
+            radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), entries.data_ptr(), point_list.data_ptr(), image.data_ptr(),
+            color.data_ptr(), allmap.data_ptr(), slot_ptr, 1 if raw_activations else 0), lib)
 
     def alloc_binning(capacity):
         ent_b, pl_b = _lib.binning_sizes(lib, capacity)
@@ -356,7 +362,7 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
     # Optimistic capacity: stage 2 is enqueued before num_rendered is known on the host, so
     # the GPU never idles behind the read-back; an overflow (rare) just re-runs stage 2.
     state = _launch_forward(device, lib, 1, P, initial_capacity(P, device), raster_settings.debug,
-                            call_pre, call_render, (geom, tile, image), alloc_binning)
+                            None, call_render, (geom, tile, image), alloc_binning, call_both=call_both)
     if raster_settings.debug:
         torch.cuda.synchronize(device)
     return color, allmap, radii, state

@@ -58,3 +58,21 @@ def lara_loss_torch(output, tar_rgb, iter, ssim=None):
         stats["normal"] = normal_error.detach()
         loss = loss + normal_error * 0.2
     return loss, stats
+
+
+def decoder_layout_torch(parameters, group_centers, K, sh_dim, opacity_shift, scaling_shift, half_cell_size):
+    """Plain-torch restatement of Decoder.forward_coarse after the MLP (lightning/network.py:261-278) followed by
+    Network.get_offseted_pt (:425-429).  Returns (centers, sh, scaling, rotation, opacity)."""
+    parameters = parameters.view(*parameters.shape[:-1], K, -1)
+    offset, sh, opacity, scaling, rotation = torch.split(parameters, [3, sh_dim, 1, 2, 4], dim=-1)
+    opacity = opacity + opacity_shift
+    scaling = scaling + scaling_shift
+    offset = torch.sigmoid(offset) * 2 - 1.0
+    B = opacity.shape[0]
+    sh = sh.view(B, -1, sh_dim // 3, 3)
+    opacity = opacity.view(B, -1, 1)
+    scaling = scaling.view(B, -1, 2)
+    rotation = rotation.view(B, -1, 4)
+    offset = offset.view(B, -1, 3)
+    centers = group_centers.reshape(1, -1, 3).unsqueeze(-2).expand(B, -1, K, -1).reshape(offset.shape) + offset * half_cell_size
+    return centers, sh, scaling, rotation, opacity

@@ -44,20 +44,23 @@ def _octagon(T, centre, opac):
         dr = [r2, r2, f32(1.41421357) * r2, f32(1.41421357) * r2]
         mg = [f32(0.0625), f32(0.0625), f32(0.0884), f32(0.0884)]
         for k in range(4):
-            r = rows[k]
+            # rows translated to the splat's screen centre (row - centre * Tw): in absolute pixel coordinates
+            # c*c - (...) cancels catastrophically at 1024^2 (round-2 finding, see preprocess.cu)
+            r = (rows[k] - dc[k][:, None] * Tw).astype(f32)
             c = (tau * (r[:, 0] * Tw[:, 0] + r[:, 1] * Tw[:, 1]) - r[:, 2] * Tw[:, 2]) * iq
             h = np.sqrt(np.maximum(f32(0.0), c * c - (tau * (r[:, 0] ** 2 + r[:, 1] ** 2) - r[:, 2] ** 2) * iq))
-            l0 = np.minimum(dc[k] - dr[k], c - h); h0 = np.maximum(dc[k] + dr[k], c + h)
-            m = mg[k] + f32(1.0e-3) * (h0 - l0)
+            l0 = np.minimum(-dr[k], c - h); h0 = np.maximum(dr[k], c + h)
+            m = mg[k] + f32(1.0e-3) * (h0 - l0) + f32(4.0e-7) * (np.abs(rows[k][:, 2]) + np.abs(dc[k] * Tw[:, 2])) * np.abs(Tw[:, 2] * iq)
             bounded = vis & (qw < 0)
-            lo[:, k] = np.where(bounded, l0 - m - dc[k], np.where(vis, f32(-3.0e38), f32(3.0e38)))
-            hi[:, k] = np.where(bounded, h0 + m - dc[k], np.where(vis, f32(3.0e38), f32(-3.0e38)))
+            lo[:, k] = np.where(bounded, l0 - m, np.where(vis, f32(-3.0e38), f32(3.0e38)))
+            hi[:, k] = np.where(bounded, h0 + m, np.where(vis, f32(3.0e38), f32(-3.0e38)))
     return _half_outward(lo, hi)
 
 
-def _valid_pairs(T, centre, opac, H, W):
-    """[P,H,W] bool: the pair is blended by the reference (forward.cu:353-398 predicates)."""
-    ys, xs = np.meshgrid(np.arange(H, dtype=f32) + f32(0.5), np.arange(W, dtype=f32) + f32(0.5), indexing="ij")
+def _valid_pairs(T, centre, opac, H, W, x0=0, y0=0):
+    """[P,H,W] bool: the pair is blended by the reference (forward.cu:353-398 predicates); pixels of the
+    H x W window whose first pixel is (x0, y0)."""
+    ys, xs = np.meshgrid(np.arange(y0, y0 + H, dtype=f32) + f32(0.5), np.arange(x0, x0 + W, dtype=f32) + f32(0.5), indexing="ij")
     px, py = xs[None], ys[None]
     g = lambda i: T[:, i][:, None, None]
     with np.errstate(all="ignore"):
@@ -113,3 +116,39 @@ def test_no_blended_pair_lies_outside_its_octagon(seed, needles, scale):
     assert valid.sum() > 1000
     # (thin oblique ellipses are where an octagon is loosest: ~0.25 for the needle scenes, ~0.6 otherwise)
     assert valid.sum() / max(int(inside.sum()), 1) > (0.15 if needles else 0.35)
+
+
+@pytest.mark.parametrize("x0,y0,seed", [(720, 730, 0), (700, 250, 1), (250, 740, 2)])
+def test_octagon_is_conservative_far_from_the_origin_and_for_faint_splats(x0, y0, seed):
+    """Windows of a 1024 x 1024 view (pixel coordinates ~1000, along the diagonals ~2000) with opacities just above
+    the 1/255 threshold: tiny tau-ellipses, where an extent computed in absolute coordinates loses all its digits
+    (round 2: two wrongly culled pairs in a 262 144-splat 1024^2 view)."""
+    size, win = 1024, 64
+    P = 60000
+    sc = S.scene(P, seed)
+    g = torch.Generator().manual_seed(seed)
+    faint = torch.rand((P, 1), generator=g) * 0.03 + 0.0035                            # tau in [~0, 4]
+    barely = (1.0 / 255.0) * (1.0 + torch.rand((P, 1), generator=g) * 0.08)            # tau in [0, 0.16]: extents of ~1 px
+    sc["opacities"] = torch.where(torch.rand((P, 1), generator=g) < 0.5, faint, barely).float()
+    sc["scales"] = sc["scales"] * 0.6
+    cam = S.cameras(3, size, size, seed)[seed % 3]
+    O.load()
+    run = O.run_scene(sc, cam, torch.ones(3))
+    centre_all = np.asarray(run.center).astype(f32)
+    vis = (np.asarray(run.radii) > 0) & (centre_all[:, 0] > x0 - 10) & (centre_all[:, 0] < x0 + win + 10) & \
+          (centre_all[:, 1] > y0 - 10) & (centre_all[:, 1] < y0 + win + 10)
+    assert vis.sum() > 100
+    T = np.asarray(run.transMat)[vis].astype(f32)
+    centre = centre_all[vis]
+    opac = sc["opacities"].numpy().reshape(-1)[vis].astype(f32)
+    lo, hi = _octagon(T, centre, opac)
+    valid, px, py = _valid_pairs(T, centre, opac, win, win, x0, y0)
+    eps = f32(0.0009765625)
+    c = lambda a: a[:, None, None]
+    coords = [px - c(centre[:, 0]), py - c(centre[:, 1]),
+              (px + py) - c(centre[:, 0] + centre[:, 1]), (px - py) - c(centre[:, 0] - centre[:, 1])]
+    inside = np.ones_like(valid)
+    for k in range(4):
+        inside &= (coords[k] >= c(lo[:, k]) - eps) & (coords[k] <= c(hi[:, k]) + eps)
+    assert valid.sum() > 300
+    assert int((valid & ~inside).sum()) == 0, f"{int((valid & ~inside).sum())} blended pairs outside the cull octagon"
