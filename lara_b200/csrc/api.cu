@@ -116,7 +116,7 @@ int bwd_variant() {
     static const int v = [] {
         const char* e = getenv("SRF_BWD_VARIANT");
         const int x = e ? atoi(e) : 2;
-        return (x >= 1 && x <= 5) ? x : 2;
+        return (x >= 1 && x <= 7) ? x : 2;
     }();
     return v;
 }

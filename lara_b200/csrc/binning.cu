@@ -58,25 +58,33 @@ __device__ __forceinline__ void bitonic_sort_cta(Ptr data, int n, int tid, int n
 
 constexpr int kSortSmallThreads = 256;
 
+constexpr int kScanCache = 8192;   // tiles whose counts the scan keeps in shared memory (2048 x 1024 px images)
+
 __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_cnt[kScanCache];
     {   // view of this CTA: own geom / tile workspace and binning buffers
         const int view = blockIdx.y;
-        a.depths = view_ptr(a.depths, view, a.geom_stride);
-        a.rects = view_ptr(a.rects, view, a.geom_stride);
         a.tile_count = view_ptr(a.tile_count, view, a.tile_stride);
         a.ranges = view_ptr(a.ranges, view, a.tile_stride);
         a.counters = view_ptr(a.counters, view, a.tile_stride);
         a.big_list = view_ptr(a.big_list, view, a.tile_stride);
         a.tile_order = view_ptr(a.tile_order, view, a.tile_stride);
-        a.entries = view_ptr(a.entries, view, a.entries_stride);
-        a.point_list = view_ptr(a.point_list, view, a.plist_stride);
     }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // The counters sit in one 256-byte block per tile (so that K1's atomics spread over the L2 slices): every read
+    // is its own sector and a full L2 round trip.  The kernel needs each count four times (scan, ranges, LPT maximum,
+    // LPT buckets); they are fetched ONCE, all loads of a thread in flight together, and kept in shared memory.
+    const bool cached = a.ntiles <= kScanCache;
+    if (cached) {
+        for (int t = tid; t < a.ntiles; t += 1024) s_cnt[t] = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+        __syncthreads();
+    }
+    auto count_of = [&](int t) -> uint32_t { return cached ? s_cnt[t] : a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE]; };
     const int chunk = (a.ntiles + 1023) / 1024;
     const int begin = min(tid * chunk, a.ntiles), end = min(begin + chunk, a.ntiles);
     uint32_t local = 0;
-    for (int t = begin; t < end; ++t) local += a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+    for (int t = begin; t < end; ++t) local += count_of(t);
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
     __syncthreads();
     uint32_t running = s_warp[wid] + incl - local;
     for (int t = begin; t < end; ++t) {
-        const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+        const uint32_t c = count_of(t);
         a.ranges[t] = c ? make_uint2(running, running + c) : make_uint2(0u, 0u);
         a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE + 1] = running;   // bucket cursor
         if (c > (uint32_t)kSmallCap) {
@@ -118,14 +126,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
         if (tid == 0) s_max = 0;
         __syncthreads();
         uint32_t lmax = 0;
-        for (int t = tid; t < a.ntiles; t += 1024) lmax = max(lmax, a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE]);
+        for (int t = tid; t < a.ntiles; t += 1024) lmax = max(lmax, count_of(t));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         if (lane == 0) atomicMax(&s_max, lmax);
         __syncthreads();
         const uint32_t cmax = s_max + 1;
         for (int t = tid; t < a.ntiles; t += 1024) {
-            const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+            const uint32_t c = count_of(t);
             const uint32_t bkt = 63u - (uint32_t)(((uint64_t)c * 64u) / cmax);   // heavy tiles -> low buckets
             atomicAdd(&s_bucket[bkt], 1u);
         }
@@ -144,16 +152,11 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
         }
         __syncthreads();
         for (int t = tid; t < a.ntiles; t += 1024) {
-            const uint32_t c = a.tile_count[(size_t)t * SRF_TILE_CTR_STRIDE];
+            const uint32_t c = count_of(t);
             const uint32_t bkt = 63u - (uint32_t)(((uint64_t)c * 64u) / cmax);
             a.tile_order[atomicAdd(&s_bucket[bkt], 1u)] = (uint32_t)t;
         }
     }
-}
-
-__device__ __forceinline__ void emit_instance(const BinArgs& a, int tile, uint64_t key) {
-    const uint32_t slot = atomicAdd(&a.tile_count[(size_t)tile * SRF_TILE_CTR_STRIDE + 1], 1u);
-    if (slot < a.capacity) a.entries[slot] = key;
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
@@ -196,7 +199,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
         for (int k = 0; k < kSerialMax; ++k)
             if (k < ntiles && slot[k] < a.capacity) a.entries[slot[k]] = key;
     }
+    // rectangles of more than kSerialMax tiles: the warp shares the work, 32 tiles per step.  Every step is
+    // "claim (returning atomic) -> store"; the stores of one step are issued only after the claims of the NEXT step
+    // are in flight, so a warp with several large splats pays one atomic round trip, not one per splat.
     unsigned big = __ballot_sync(0xffffffffu, ntiles > kSerialMax);
+    uint32_t pend_slot = 0xffffffffu;
+    uint64_t pend_key = 0;
     while (big) {
         const int src = __ffs(big) - 1;
         big &= big - 1;
@@ -204,11 +212,17 @@ __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
         const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
         const uint64_t bkey = __shfl_sync(0xffffffffu, key, src);
         const int w = bx1 - bx0, n = w * (by1 - by0);
-        for (int t = lane; t < n; t += 32) {
-            const int ty = t / w, tx = t - ty * w;
-            emit_instance(a, (by0 + ty) * a.gx + bx0 + tx, bkey);
+        for (int t = lane; t < n + lane; t += 32) {          // same trip count for all lanes of the warp
+            uint32_t slot = 0xffffffffu;
+            if (t < n) {
+                const int ty = t / w, tx = t - ty * w;
+                slot = atomicAdd(&a.tile_count[(size_t)((by0 + ty) * a.gx + bx0 + tx) * SRF_TILE_CTR_STRIDE + 1], 1u);
+            }
+            if (pend_slot < a.capacity) a.entries[pend_slot] = pend_key;      // previous step's store
+            pend_slot = slot; pend_key = bkey;
         }
     }
+    if (pend_slot < a.capacity) a.entries[pend_slot] = pend_key;
 }
 
 // Per-tile sort: a monotone depth-bucket sort.

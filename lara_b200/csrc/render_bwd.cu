@@ -56,8 +56,8 @@ __device__ __forceinline__ float ex2_fast(float x) {
 // Pair evaluation of phase 1.  What must agree with the forward BIT FOR BIT are the accept / reject decisions
 // (a pair taken by one pass and not by the other shifts the whole transmittance chain of its pixel); the values
 // only need ~1e-6.  So the two IEEE divisions and expf() of eval_pair() become MUFU.RCP / MUFU.EX2 (<= 2 ulp), and a
-// pair that lands within a 1e-5 relative band of a decision threshold (alpha = 1/255, depth = 0.2) -- one in ~1e5 --
-// is re-evaluated with the forward's exact sequence.  k, l and p = k x l are the forward's own operations, so the
+// pair that lands within a 1e-4 / 1e-5 relative band of a decision threshold (alpha = 1/255, depth = 0.2, rho3d = rho2d)
+// -- one in ~1e4 -- is re-evaluated with the forward's exact sequence.  k, l and p = k x l are the forward's own operations, so the
 // p.z != 0 test is exact as is.
 struct PairBwd {
     float depth, G, alpha;
@@ -92,7 +92,11 @@ __device__ __forceinline__ void eval_pair_bwd(const float4 q0, const float4 q1, 
     const float araw = q2.w * r.G;
     r.alpha = fminf(0.99f, araw);
     r.valid = (pz != 0.0f) && !(r.depth < SRF_NEAR_F) && !(araw < 0.00392156862745098f);
-    const bool near_thr = fabsf(araw - 0.00392156862745098f) < 4.0e-8f || fabsf(r.depth - SRF_NEAR_F) < 2.0e-6f;
+    // decisions of the forward that the approximate values could take differently: alpha vs 1/255, depth vs the
+    // near plane, and WHICH of the two footprints is the smaller one (rho3d vs rho2d picks the gradient path: a splat
+    // whose projected sigma is ~0.707 px has rho3d ~ rho2d at every pixel)
+    const bool near_thr = fabsf(araw - 0.00392156862745098f) < 4.0e-7f || fabsf(r.depth - SRF_NEAR_F) < 2.0e-5f ||
+                          fabsf(rho3d - rho2d) <= 1.0e-5f * rho2d;
     if (near_thr && pz != 0.0f) {
         PairEval e;
         eval_pair(q0, q1, q2, pixx, pixy, e);
@@ -100,25 +104,27 @@ __device__ __forceinline__ void eval_pair_bwd(const float4 q0, const float4 q1, 
     }
 }
 
-template <int BATCH>
+template <int BATCH, int NW>
 struct BwdSmem {
     static constexpr size_t rec = 0;                                                         // float4 [6][BATCH]
     static constexpr size_t x = rec + sizeof(float4) * SRF_REC_QUADS * BATCH;                // float [warps][3][16][32]
-    static constexpr size_t pixA = x + sizeof(float) * SRF_CTA_WARPS * 3 * kBwdGroup * 32;   // float4 [256] dn0 dn1 dn2 dpix0
-    static constexpr size_t pixB = pixA + sizeof(float4) * SRF_CTA_THREADS;                  // float4 [256] dpix1 dpix2 dL_ddepth dL_dalpha
-    static constexpr size_t list = pixB + sizeof(float4) * SRF_CTA_THREADS;                  // uint8 [warps][BATCH]
-    static constexpr size_t wmax = list + (size_t)SRF_CTA_WARPS * BATCH;                     // int [warps]
-    static constexpr size_t total = wmax + sizeof(int) * SRF_CTA_WARPS;
+    static constexpr size_t pixA = x + sizeof(float) * NW * 3 * kBwdGroup * 32;              // float4 [threads] dn0 dn1 dn2 dpix0
+    static constexpr size_t pixB = pixA + sizeof(float4) * NW * 32;                          // float4 [threads] dpix1 dpix2 dL_ddepth dL_dalpha
+    static constexpr size_t list = pixB + sizeof(float4) * NW * 32;                          // uint8 [warps][BATCH]
+    static constexpr size_t wmax = list + (size_t)NW * BATCH;                                // int [warps]
+    static constexpr size_t total = wmax + sizeof(int) * 8;
 };
 
 // EXACT : phase 1 evaluates pairs with the forward's exact sequence (else approximate + exact re-check at thresholds)
 // P2WALK: every phase-2 lane walks its own contributing pixels (else all lanes step through the 16 pixels together)
 // SMEMC : phase 1 reads the pixel's upstream gradients from shared memory (eight registers less)
-template <int BATCH, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
-__global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(RenderBwdArgs a) {
+// NW    : warps per CTA -- 8 = one CTA per 16x16 tile, 4 = one CTA per 16x8 half tile (two CTAs walk the tile's list)
+template <int BATCH, int NW, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
+__global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs a) {
     static_assert(BATCH <= 256, "hit lists are uint8");
     extern __shared__ __align__(16) unsigned char smem[];
-    typedef BwdSmem<BATCH> L;
+    typedef BwdSmem<BATCH, NW> L;
+    constexpr int NT = NW * 32;
     float4 (*s_rec)[BATCH] = reinterpret_cast<float4 (*)[BATCH]>(smem + L::rec);
     float4* s_pixA = reinterpret_cast<float4*>(smem + L::pixA);
     float4* s_pixB = reinterpret_cast<float4*>(smem + L::pixB);
@@ -141,16 +147,17 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
     a.dL_dothers += (size_t)view * 8 * npix;
     a.ggrad = view_ptr(a.ggrad, view, a.ggrad_stride);
 
-    const int tile = (int)a.tile_order[blockIdx.x];
+    const int tile = (int)a.tile_order[blockIdx.x / (8 / NW)];
+    const int gw = (int)(blockIdx.x % (8 / NW)) * NW + wid;       // which of the tile's eight 8x4 blocks
     const int tyi = tile / a.gx, txi = tile - tyi * a.gx;
     int lx, ly;
-    tile_pixel(tid, lx, ly);
+    tile_pixel(gw * 32 + lane, lx, ly);
     const int pxi = txi * SRF_TILE + lx, pyi = tyi * SRF_TILE + ly;
     const bool inside = pxi < a.W && pyi < a.H;
     const size_t pix = (size_t)pyi * a.W + pxi;
     // first pixel centre of this warp's 8x4 block; the block's bounds are rebuilt from it where needed
     // (two live registers instead of eight)
-    const float bx0 = (float)(txi * SRF_TILE + ((wid & 1) << 3)) + 0.5f, by0 = (float)(tyi * SRF_TILE + ((wid >> 1) << 2)) + 0.5f;
+    const float bx0 = (float)(txi * SRF_TILE + ((gw & 1) << 3)) + 0.5f, by0 = (float)(tyi * SRF_TILE + ((gw >> 1) << 2)) + 0.5f;
 
     uint2 range = a.ranges[tile];
     if (range.y > a.capacity) range.y = range.x;
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
     __syncthreads();
     int n_eff = 0;
 #pragma unroll
-    for (int w = 0; w < SRF_CTA_WARPS; ++w) n_eff = max(n_eff, s_wmax[w]);
+    for (int w = 0; w < NW; ++w) n_eff = max(n_eff, s_wmax[w]);
     const int rounds = (n_eff + BATCH - 1) / BATCH;
 
     // accum_rec / last_* recursions of backward.cu:331-385, two channels per packed fp32x2 register:
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
     for (int b = 0; b < rounds; ++b) {
         // ---- stage batch b (back to front: slot j holds list position n_eff-1-(b*BATCH+j))
         __syncthreads();                                  // every warp is done with the previous batch's records
-        for (int jt = tid; jt < BATCH; jt += SRF_CTA_THREADS) {
+        for (int jt = tid; jt < BATCH; jt += NT) {
             const int pos = n_eff - 1 - (b * BATCH + jt);
             if (pos >= 0) {
                 const uint32_t id = __ldg(a.point_list + range.x + pos);
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                 const float* xrow = s_xw + p2_i * 32;
                 const float ybase = by0 + (float)(2 * p2_h);
                 const int pbase = wid * 32 + 16 * p2_h;
+#pragma unroll 1
                 for (int it = 0; it < iters2; ++it) {
                     int t;
                     if (P2WALK) {
@@ -394,20 +402,20 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
                         const f32x2 Dx = fma2(Sy, bc2(dpz), mul2(Sz, bc2(-dp.y)));
                         const f32x2 Dy = fma2(Sz, bc2(dp.x), mul2(Sx, bc2(-dpz)));
                         const f32x2 Dz = fma2(Sx, bc2(dp.y), mul2(Sy, bc2(-dp.x)));
-                        A0 = add2(A0, Dx); A1 = add2(A1, Dy); A2 = add2(A2, Dz);
+                        add2_acc(A0, Dx); add2_acc(A1, Dy); add2_acc(A2, Dz);
                         // dL_dTw = pix.x dk + pix.y dl + dL_dz (s, 1)  (record holds -dl, hence -pix.y)
                         const float2 Dx_ = up2(Dx), Dy_ = up2(Dy), Dz_ = up2(Dz);
                         f32x2 tw67 = mul2(S, bc2(dL_dz));
                         tw67 = fma2(bc2(ppx), pk2(Dx_.x, Dy_.x), tw67);
                         tw67 = fma2(bc2(-ppy), pk2(Dx_.y, Dy_.y), tw67);
-                        A3 = add2(A3, tw67);
+                        add2_acc(A3, tw67);
                         const float tw8 = fmaf(ppx, Dz_.x, fmaf(-ppy, Dz_.y, dL_dz));
-                        A4 = add2(A4, pk2(tw8, GdA));
+                        add2_acc(A4, pk2(tw8, GdA));
                     } else {
                         // low-pass branch (backward.cu:436-443); FilterInvSquare == 2 after fp32 rounding
                         const f32x2 d = sub2(cen, pix2);
                         fma2_acc(A8, d, bc2(2.0f * nopac * GdA));
-                        A4 = add2(A4, pk2(dL_dz, GdA));
+                        add2_acc(A4, pk2(dL_dz, GdA));
                     }
                 }
                 // combine the two half blocks and send the totals out: lanes of half 0 own record quads 0,1
@@ -440,13 +448,13 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, MINB) render_bwd_kernel(Rende
 
 cudaError_t launch_render_bwd_v1(const RenderBwdArgs& a, cudaStream_t stream);
 
-template <int B, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
-static cudaError_t launch_variant(const RenderBwdArgs& a, dim3 grid, cudaStream_t stream) {
-    auto k = render_bwd_kernel<B, MINB, EXACT, P2WALK, SMEMC>;
+template <int B, int NW, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
+static cudaError_t launch_variant(const RenderBwdArgs& a, cudaStream_t stream) {
+    auto k = render_bwd_kernel<B, NW, MINB, EXACT, P2WALK, SMEMC>;
     // the opt-in is per device (and cheap): made on every call for the current device
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B>::total);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B, NW>::total);
     if (e != cudaSuccess) return e;
-    k<<<grid, SRF_CTA_THREADS, BwdSmem<B>::total, stream>>>(a);
+    k<<<dim3(a.gx * a.gy * (8 / NW), a.nviews), NW * 32, BwdSmem<B, NW>::total, stream>>>(a);
     return cudaSuccess;
 }
 
@@ -457,12 +465,13 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     if (variant == 1) return launch_render_bwd_v1(a, stream);
     prof_start(K_RENDER_BWD, stream);
     cudaError_t e = cudaSuccess;
-    const dim3 grid(ntiles, a.nviews);
     switch (variant) {
-        case 3: e = launch_variant<160, 3, false, true, true>(a, grid, stream); break;
-        case 4: e = launch_variant<256, 2, false, false, false>(a, grid, stream); break;
-        case 5: e = launch_variant<256, 2, true, true, false>(a, grid, stream); break;
-        default: e = launch_variant<256, 2, false, true, false>(a, grid, stream); break;
+        case 3: e = launch_variant<160, 8, 3, false, true, true>(a, stream); break;
+        case 4: e = launch_variant<256, 8, 2, false, false, false>(a, stream); break;
+        case 5: e = launch_variant<256, 8, 2, true, true, false>(a, stream); break;
+        case 6: e = launch_variant<256, 4, 4, false, true, false>(a, stream); break;      // half-tile CTAs
+        case 7: e = launch_variant<128, 4, 5, false, true, false>(a, stream); break;      // half-tile CTAs, 128-splat rounds
+        default: e = launch_variant<256, 8, 2, false, true, false>(a, stream); break;
     }
     prof_stop(K_RENDER_BWD, stream);
     return e != cudaSuccess ? e : cudaGetLastError();

@@ -17,7 +17,8 @@ namespace srf {
 
 __global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) render_fwd_kernel(RenderFwdArgs a) {
     __shared__ float4 s_rec[SRF_REC_QUADS][SRF_BATCH];
-    __shared__ uint32_t s_mask[SRF_CTA_WARPS][SRF_BATCH_CHUNKS][32];   // [warp][chunk of 32 splats][lane]: per-pixel hit words
+    __shared__ uint32_t s_mask[SRF_CTA_WARPS][SRF_BATCH_CHUNKS][32];   // [warp][group of 32 hits][lane]: per-pixel hit words
+    __shared__ uint8_t s_list[SRF_CTA_WARPS][SRF_BATCH];               // [warp]: batch slots of the splats that can touch the warp's block
 
     const int tid = threadIdx.x;
     {   // view of this CTA: per-view workspaces of identical layout, images stacked [V,C,H,W]
@@ -76,17 +77,30 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) rende
         const int cnt = min(SRF_BATCH, todo);
         // warp-uniform skip: a fully saturated warp only helps with staging
         if (__all_sync(0xffffffffu, done)) continue;
-        const int nchunks = (cnt + 31) >> 5;
-
-        // ---- phase A: per-pixel hit masks.  Lane l takes splat c*32+l and rasterises its conservative
-        // alpha >= 1/255 octagon over the warp's 8x4 pixel block into a 32-bit mask (bit = lane that owns
-        // the pixel); a 32x32 bit transpose over the warp then hands every lane the word "which of these
-        // 32 splats can touch MY pixel".  A splat outside a pixel's word cannot reach alpha >= 1/255
-        // there, so skipping it changes no result.
+        // ---- phase A: per-pixel hit masks.  First a warp-level cull: the staged splats whose conservative
+        // alpha >= 1/255 octagon can touch this warp's 8x4 block at all (~1 in 5) are compacted into a list, in list
+        // order.  Then, 32 hits at a time, lane l rasterises the octagon of hit g*32+l over the block into a 32-bit
+        // mask (bit = lane that owns the pixel) and a 32x32 bit transpose over the warp hands every lane the word
+        // "which of these 32 splats can touch MY pixel".  A splat outside a pixel's word cannot reach
+        // alpha >= 1/255 there, so skipping it changes no result.
+        int nh = 0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int jt = c0 + lane;
+            const bool hit = (jt < cnt) && octagon_hits(s_rec[2][jt], s_rec[5][jt], wrect);
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (hit) s_list[wid][nh + __popc(hits & ((1u << lane) - 1u))] = (uint8_t)jt;
+            nh += __popc(hits);
+        }
+        __syncwarp();
+        const int nchunks = (nh + 31) >> 5;
+        if (nchunks == 0) continue;
         for (int c = 0; c < nchunks; ++c) {
-            const int jt = (c << 5) + lane;
+            const int h = (c << 5) + lane;
             uint32_t m = 0;
-            if (jt < cnt) m = octagon_pixel_mask(s_rec[2][jt], s_rec[5][jt], wrect);
+            if (h < nh) {
+                const int jt = s_list[wid][h];
+                m = octagon_pixel_mask(s_rec[2][jt], s_rec[5][jt], wrect);
+            }
             s_mask[wid][c][lane] = transpose32(m, lane);
         }
         __syncwarp();
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(SRF_CTA_THREADS, 1024 / SRF_CTA_THREADS) rende
             const bool active = (w != 0);
             if (!__any_sync(0xffffffffu, active)) break;
             if (!active) continue;
-            const int j = (c << 5) + __ffs(w) - 1;
+            const int j = s_list[wid][(c << 5) + __ffs(w) - 1];
             w &= w - 1;
             contributor = (uint32_t)(b * SRF_BATCH + j + 1);
             PairEval e;
