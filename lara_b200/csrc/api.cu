@@ -115,8 +115,8 @@ void prof_stop(int kernel, cudaStream_t stream) {
 int bwd_variant() {
     static const int v = [] {
         const char* e = getenv("SRF_BWD_VARIANT");
-        const int x = e ? atoi(e) : 2;
-        return (x >= 1 && x <= 7) ? x : 2;
+        const int x = e ? atoi(e) : 7;
+        return (x >= 1 && x <= 8) ? x : 7;
     }();
     return v;
 }

@@ -116,10 +116,12 @@ struct BwdSmem {
 };
 
 // EXACT : phase 1 evaluates pairs with the forward's exact sequence (else approximate + exact re-check at thresholds)
-// P2WALK: every phase-2 lane walks its own contributing pixels (else all lanes step through the 16 pixels together)
+// P2WALK: 0 = all phase-2 lanes step through the 16 pixels of their half block together; 1 = every lane walks the
+//         contributing pixels of its own half block; 2 = the two lanes of a splat share ALL its contributing pixels
+//         alternately (a splat that only touches one half block no longer leaves its other lane idle)
 // SMEMC : phase 1 reads the pixel's upstream gradients from shared memory (eight registers less)
 // NW    : warps per CTA -- 8 = one CTA per 16x16 tile, 4 = one CTA per 16x8 half tile (two CTAs walk the tile's list)
-template <int BATCH, int NW, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
+template <int BATCH, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC>
 __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs a) {
     static_assert(BATCH <= 256, "hit lists are uint8");
     extern __shared__ __align__(16) unsigned char smem[];
@@ -342,8 +344,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                 const uint32_t word = __shfl_sync(0xffffffffu, tw, p2_i);
                 const bool have = gbase + p2_i < nh;
                 uint32_t mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
+                if (P2WALK == 2) {
+                    mybits = have ? word : 0u;
+                    if (p2_h) mybits &= mybits - 1;        // the second lane of a splat starts at its second pixel
+                }
                 uint32_t tmask = __reduce_or_sync(0xffffffffu, mybits);
-                const int iters2 = P2WALK ? (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(mybits)) : __popc(tmask);
+                const int iters2 = P2WALK == 2 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mybits) + 1) >> 1)
+                                 : P2WALK == 1 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(mybits)) : __popc(tmask);
                 if (iters2 == 0) continue;
                 const int j2 = have ? (int)lst[p2_i] : 0;
                 const float4 q0 = s_rec[0][j2], q1 = s_rec[1][j2], q2 = s_rec[2][j2];
@@ -356,12 +363,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                 // (DN0,DN1) (DN2,DC0) (DC1,DC2) (DM0,DM1)
                 f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull, A3 = 0ull, A4 = 0ull, A5 = 0ull, A6 = 0ull, A7 = 0ull, A8 = 0ull;
                 const float* xrow = s_xw + p2_i * 32;
-                const float ybase = by0 + (float)(2 * p2_h);
-                const int pbase = wid * 32 + 16 * p2_h;
+                const float ybase = by0 + (P2WALK == 2 ? 0.0f : (float)(2 * p2_h));
+                const int pbase = wid * 32 + (P2WALK == 2 ? 0 : 16 * p2_h);
 #pragma unroll 1
                 for (int it = 0; it < iters2; ++it) {
                     int t;
-                    if (P2WALK) {
+                    if (P2WALK == 2) {
+                        if (mybits == 0) continue;
+                        t = __ffs(mybits) - 1;             // mine ...
+                        mybits &= mybits - 1;
+                        mybits &= mybits - 1;              // ... and the next one is the partner lane's
+                    } else if (P2WALK == 1) {
                         if (mybits == 0) continue;
                         t = __ffs(mybits) - 1;             // every lane walks its own contributing pixels
                         mybits &= mybits - 1;
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                         tmask &= tmask - 1;
                         if (!((mybits >> t) & 1u)) continue;
                     }
-                    const int p = t + 16 * p2_h;
+                    const int p = P2WALK == 2 ? t : t + 16 * p2_h;
                     const float ppx = bx0 + (float)(t & 7), ppy = ybase + (float)(t >> 3);
                     const float* xp = xrow + (p ^ p2_i);
                     const float ws = xp[0], GdA = xp[kBwdGroup * 32], dL_dz = xp[2 * kBwdGroup * 32];
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
 
 cudaError_t launch_render_bwd_v1(const RenderBwdArgs& a, cudaStream_t stream);
 
-template <int B, int NW, int MINB, bool EXACT, bool P2WALK, bool SMEMC>
+template <int B, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC>
 static cudaError_t launch_variant(const RenderBwdArgs& a, cudaStream_t stream) {
     auto k = render_bwd_kernel<B, NW, MINB, EXACT, P2WALK, SMEMC>;
     // the opt-in is per device (and cheap): made on every call for the current device
@@ -466,12 +478,13 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     prof_start(K_RENDER_BWD, stream);
     cudaError_t e = cudaSuccess;
     switch (variant) {
-        case 3: e = launch_variant<160, 8, 3, false, true, true>(a, stream); break;
-        case 4: e = launch_variant<256, 8, 2, false, false, false>(a, stream); break;
-        case 5: e = launch_variant<256, 8, 2, true, true, false>(a, stream); break;
-        case 6: e = launch_variant<256, 4, 4, false, true, false>(a, stream); break;      // half-tile CTAs
-        case 7: e = launch_variant<128, 4, 5, false, true, false>(a, stream); break;      // half-tile CTAs, 128-splat rounds
-        default: e = launch_variant<256, 8, 2, false, true, false>(a, stream); break;
+        case 3: e = launch_variant<160, 8, 3, false, 1, true>(a, stream); break;
+        case 4: e = launch_variant<256, 8, 2, false, 0, false>(a, stream); break;
+        case 5: e = launch_variant<256, 8, 2, true, 1, false>(a, stream); break;
+        case 6: e = launch_variant<256, 4, 4, false, 1, false>(a, stream); break;      // half-tile CTAs
+        case 2: e = launch_variant<256, 8, 2, false, 1, false>(a, stream); break;      // one CTA per tile, own-half phase-2 lanes
+        case 8: e = launch_variant<256, 8, 2, false, 2, false>(a, stream); break;      // one CTA per tile, shared phase-2 lanes
+        default: e = launch_variant<256, 4, 4, false, 2, false>(a, stream); break;     // 7: half-tile CTAs, shared phase-2 lanes
     }
     prof_stop(K_RENDER_BWD, stream);
     return e != cudaSuccess ? e : cudaGetLastError();

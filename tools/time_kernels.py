@@ -57,7 +57,7 @@ for i in range(args.steps):
     st[2 * i].record(); step(); st[2 * i + 1].record()
 torch.cuda.synchronize()
 ms = sum(st[2 * i].elapsed_time(st[2 * i + 1]) for i in range(args.steps)) / args.steps
-out = {"P": args.P, "size": args.size, "views": args.views, "bwd_variant": os.environ.get("SRF_BWD_VARIANT", "2"),
+out = {"P": args.P, "size": args.size, "views": args.views, "bwd_variant": os.environ.get("SRF_BWD_VARIANT", "7"),
        "us_per_view": {n: round(v[0] * 1e3 / max(v[1], 1) / (1 if n == "render_bwd" and os.environ.get("SRF_BWD_VARIANT") == "1" else args.views), 2)
                        for n, v in k.items()},
        "launches": {n: v[1] for n, v in k.items()},
