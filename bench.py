@@ -189,10 +189,10 @@ def cpu_baseline(P, size, budget_s=10.0, max_views=8):
 class Workload:
     """Resident inputs of one configuration: parameters, per-view settings, packed cameras, stacked upstream grads."""
 
-    def __init__(self, P, size, view_ids, total_views, dev, settings_cls):
+    def __init__(self, P, size, view_ids, total_views, dev, settings_cls, seed=0):
         from lara_b200 import scene as S
         self.P, self.size, self.ids = P, size, list(view_ids)
-        self.sc = S.scene(P, 0, sh_degree=1)
+        self.sc = S.scene(P, seed, sh_degree=1)
         self.cams = S.cameras(total_views, size, size, 0)
         gc, ga = S.upstream_grads(size, size, 0, lara_like=True)
         self.gc, self.ga = gc.to(dev), ga.to(dev)
@@ -335,6 +335,8 @@ def host_buffers(wl, grads_numel):
     return (pinned, cam_host, host_out), h2d, host_out.numel() * 4
 
 
+C3_SCENES = 8
+
 EXTRA_CONFIGS = [      # name, P, size, views per GPU   (BASELINE.json configs[1] and configs[3])
     ("C2_32k_512_1view", 32768, 512, 1),
     ("C4_256k_1024_4views_per_gpu", 262144, 1024, 4),
@@ -378,6 +380,9 @@ def run_reference(args, rank, local, world):
         for name, P, size, views in EXTRA_CONFIGS:
             v, m = measure(P, size, views, max(3, args.steps // 4), 3)
             extra[name] = {"value": v, "unit": UNIT, "ms_per_step": m, "views_per_step": views}
+        v, m = measure(524288, 512, 8, 2, 1)              # one scene's 8 views; a step of C3 is 8 such scenes
+        extra["C3_raster_share_524k_8views_per_scene"] = {"value": v, "unit": UNIT, "ms_per_step": m * C3_SCENES, "scenes_per_gpu": C3_SCENES,
+                                                          "views_per_scene": 8, "note": "timed on one scene (8 views), step time scaled to 8 scenes"}
         v, m = measure(args.P, args.size, 8, max(3, args.steps // 2), 3)
         extra["strong_8_global_views"] = {"value": v, "unit": UNIT, "ms_per_step": m, "views_per_step": 8,
                                           "note": "the reference is single-GPU: all 8 views on one B200"}
@@ -462,6 +467,9 @@ def main():
     e2e_value = total_views * e2e_steps / (ms_e2e / 1e3)
     ms_e2b, _ = timed_steps(make_batched_e2e_step(wl, host_io, world), e2e_steps, 3, flush, world, dev)
     e2e_batched = total_views * e2e_steps / (ms_e2b / 1e3)
+    # the per-view drop-in API with resident inputs (no host copies): separates "one launch set per view" from the copies
+    ms_dr, _ = timed_steps(make_dropin_step(wl, DSR), e2e_steps, 3, flush, world, dev)
+    dropin_resident = total_views * e2e_steps / (ms_dr / 1e3)
     clocks = sampler.stop() if sampler else None
 
     # ---- extra configurations: C2, C4, strong-scaling point, sustained run
@@ -481,6 +489,23 @@ def main():
                 entry["dropin_api_ms_per_view"] = m2 / (4 * ks)
             extra[name] = entry
             del wle, ge
+        # C3 / C5 (BASELINE configs[2], [4]): the rasterizer share of a LaRa train step -- 8 target views per scene at LaRa's
+        # own Gaussian count, 8 scenes on one GPU (C3) or 32 scenes over 8 GPUs = 4 per GPU (C5); scenes are data-parallel
+        # (the DDP all-reduce of the NETWORK gradients is outside this path), so no collective inside the step
+        n_sc = C3_SCENES if world == 1 else max(1, 32 // world)
+        wls = [Workload(524288, 512, range(8), 8, dev, R.GaussianRasterizationSettings, seed=sd) for sd in range(min(n_sc, 2))]
+        gsc = sharded.GradBuffer(524288, wls[0].M, dev)
+        steps_sc = [make_batched_step(w_, gsc, all_reduce=False) for w_ in wls]
+
+        def step_scenes():
+            for k in range(n_sc):
+                steps_sc[k % len(steps_sc)]()
+        ks = max(2, args.steps // 5)
+        m, _ = timed_steps(step_scenes, ks, 2, flush, world, dev)
+        extra["C3_raster_share_524k_8views_per_scene"] = {
+            "value": n_sc * 8 * world * ks / (m / 1e3), "unit": UNIT, "ms_per_step": m / ks, "scenes_per_gpu": n_sc,
+            "views_per_scene": 8, "note": "rasterizer fwd+bwd share of the train step (network, loss and DDP all-reduce are outside the path)"}
+        del wls, gsc, steps_sc
         if 8 % world == 0:
             ids = sharded.shard_views(8, rank, world)
             wls = Workload(args.P, args.size, ids, 8, dev, R.GaussianRasterizationSettings)
@@ -586,6 +611,8 @@ def main():
                        "l2": "flushed between steps (256 MiB write, untimed)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "diff_surfel_rasterization.GaussianRasterizer + autograd (one view per call), pinned host in / grads out",
+                    "dropin_api_inputs_resident": {"value": dropin_resident, "unit": UNIT,
+                                                   "api": "the same per-view autograd API without the host copies (what the reference arm measures)"},
                     "batched": {"value": e2e_batched, "unit": UNIT,
                                 "api": "same host-in/host-out protocol, one autograd node + one launch set per scene (srf_views_*)"}},
             "gpu_launches": KERNELS_PER_STEP * args.steps * world,

@@ -294,9 +294,22 @@ int forward_preprocess_impl(const char* fn, cudaStream_t stream, int V, int P, i
         e = srf::launch_preprocess_fwd(a, stream);
         if (e != cudaSuccess) return cuda_fail("preprocess_fwd launch", e);
     }
+    // num_rendered read-back: pinned host memory is device-visible under UVA, so the scan kernel stores the counts there
+    // itself (no copy-engine operation between the kernels of the stream); pageable memory falls back to an async copy
+    bool zero_copy = false;
+    if (num_rendered_host) {
+        cudaPointerAttributes at_;
+        if (cudaPointerGetAttributes(&at_, num_rendered_host) == cudaSuccess && at_.type == cudaMemoryTypeHost &&
+            at_.devicePointer != nullptr) {
+            b.count_host = static_cast<uint32_t*>(at_.devicePointer);
+            zero_copy = true;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     e = srf::launch_tile_scan(b, stream);
     if (e != cudaSuccess) return cuda_fail("tile_scan launch", e);
-    if (num_rendered_host) {
+    if (num_rendered_host && !zero_copy) {
         e = cudaMemcpy2DAsync(num_rendered_host, sizeof(uint32_t), b.counters, tl.total, sizeof(uint32_t), (size_t)V,
                               cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return cuda_fail("num_rendered copy", e);

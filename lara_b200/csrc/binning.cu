@@ -102,7 +102,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(BinArgs a) {
             if (lane >= o) wi += v;
         }
         s_warp[lane] = wi - w;  // exclusive prefix of warp totals
-        if (lane == 31) a.counters[0] = wi;  // num_rendered
+        if (lane == 31) {
+            a.counters[0] = wi;  // num_rendered
+            if (a.count_host != nullptr) {          // zero-copy read-back: no copy-engine operation in the stream
+                a.count_host[blockIdx.y] = wi;
+                __threadfence_system();
+            }
+        }
     }
     __syncthreads();
     uint32_t running = s_warp[wid] + incl - local;
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(BinArgs a) {
     const int lane = threadIdx.x & 31;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0, ntiles = 0;
     uint64_t key = 0;
+
     if (idx < a.P) {
         const uint2 r = a.rects[idx];   // (0,0,0,0) for culled Gaussians
         x0 = r.x & 0xffff; y0 = r.x >> 16; x1 = r.y & 0xffff; y1 = r.y >> 16;
@@ -298,6 +305,20 @@ __device__ __forceinline__ void depth_bucket_sort(const uint64_t* __restrict__ s
         if (tid == NT - 1) s_start[NB] = run;
     }
     __syncthreads();
+    // Degenerate depth distribution (many instances share a bucket, in the limit all depths are equal): ranking inside
+    // a bucket is quadratic in its size.  Past kMaxBucket the tile falls back to the comparison network
+    // (n log^2 n whatever the keys are); the result is the same total order.
+    {
+        constexpr uint32_t kMaxBucket = 96;
+        uint32_t big = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) big = max(big, s_start[tid * PER + k + 1 > NB ? NB : tid * PER + k + 1] - s_start[tid * PER + k]);
+        if (__syncthreads_or(big > kMaxBucket)) {
+            bitonic_sort_cta(s_keys, n, tid, NT);
+            for (int i = tid; i < n; i += NT) dst[i] = (uint32_t)s_keys[i];
+            return;
+        }
+    }
     for (int i = tid; i < n; i += NT) {
         const uint64_t k = s_keys[i];
         const float d = __uint_as_float((uint32_t)(k >> 32));

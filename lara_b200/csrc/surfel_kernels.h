@@ -58,6 +58,7 @@ struct BinArgs {
     uint32_t* tile_count;        // [ntiles * SRF_TILE_CTR_STRIDE]: word 0 count, word 1 bucket cursor
     uint2* ranges;               // [ntiles] out
     uint32_t* counters;          // [4]: num_rendered, big_count, overflow, spare
+    uint32_t* count_host;        // [nviews] device-visible pinned host memory: the scan stores num_rendered there directly (or null)
     uint32_t* big_list;          // [ntiles] scratch
     uint32_t* tile_order;        // [ntiles] out: tiles by descending instance count (launch order of the blend CTAs)
     uint64_t* entries;           // [capacity] scratch: depth_bits<<32 | gaussian idx, bucketed by tile

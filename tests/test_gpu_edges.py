@@ -76,6 +76,41 @@ def test_huge_splats_cover_every_tile(cuda_device, reference, n_big, expect_min)
         assert np.isfinite(mine[k]).all()
 
 
+@pytest.mark.parametrize("n,H", [(2000, 16), (8000, 16), (8000, 48)])
+def test_equal_depth_pileup_is_sorted_and_not_quadratic(cuda_device, reference, n, H):
+    """Every instance of a tile has the SAME depth (the degenerate case of the depth-bucket sort: one bucket holds the
+    whole tile, ranking inside it would be quadratic -- 8192 instances = 65k steps per thread).  The sort falls back to the
+    comparison network; order (by Gaussian index, as the reference's stable sort leaves it) and a time bound are checked."""
+    from lara_b200 import rasterizer as R, scene as S
+    from oracle import ref as REF
+    sc = S.scene(n, 9)
+    sc["means3D"][:] = torch.tensor([0.0, 0.0, 0.0])      # all splats at the origin: identical view-space depth
+    sc["scales"][:] = 0.5
+    sc["opacities"][:] = 0.01
+    cam = S.cameras(1, H, H, 0)[0]
+    bg = torch.zeros(3)
+    mine = run_candidate(sc, cam, bg, cuda_device)
+    scd = to_dev(sc, cuda_device)
+    st = S.settings_for(cam, bg, 1, cuda_device, reference.GaussianRasterizationSettings)
+    r = REF.forward_raw(reference, scd, st)
+    assert mine["num_rendered"] == r["num_rendered"] >= n
+    assert np.array_equal(mine["point_list"], r["point_list"].cpu().numpy())
+    assert len(np.unique(mine["depths"][mine["radii"] > 0].view(np.int32))) == 1
+    # time: the whole forward of this tiny image, repeated; a quadratic rank loop takes milliseconds per tile
+    stm = S.settings_for(cam, bg, 1, cuda_device, R.GaussianRasterizationSettings)
+    args = (scd["means3D"], scd["shs"], None, scd["opacities"], scd["scales"], scd["rotations"], None, stm)
+    for _ in range(3):
+        R.forward_raw(*args)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        R.forward_raw(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) / 10 < 3.0, f"{e0.elapsed_time(e1) / 10:.2f} ms per forward"
+
+
 def test_sorted_by_depth_then_index_within_each_tile(cuda_device):
     from lara_b200 import scene as S
     sc = S.scene(30000, 5)

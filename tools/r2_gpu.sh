@@ -1,15 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/time_kernels.log
-for v in 2 8 7; do
-  SRF_BWD_VARIANT=$v timeout 300 python tools/time_kernels.py >> gpurun_out/time_kernels.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+for pdl in 0 1; do
+  SRF_PDL=$pdl timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin if l.startswith('{')][-1])
+print('PDL=$pdl value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'resident dropin',round(d['e2e']['dropin_api_inputs_resident']['value'],1),'batched e2e',round(d['e2e']['batched']['value'],1))"
 done
-SRF_BWD_VARIANT=8 timeout 300 python tools/time_kernels.py --P 524288 >> gpurun_out/time_kernels.log 2>&1
-python - <<'PY'
-import json
-for l in open('gpurun_out/time_kernels.log'):
-    try:
-        d = json.loads(l); print(d['P'], d['bwd_variant'], d['us_per_view']['render_bwd'], d['us_per_view']['render_fwd'], d['views_per_s'])
-    except Exception: print(l[:200])
-PY
-for v in 8 7; do SRF_BWD_VARIANT=$v timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py tests/test_gpu_views.py tests/test_gpu_headline.py -m gpu -q -x 2>&1 | tail -2; done
