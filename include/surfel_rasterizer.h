@@ -104,7 +104,8 @@ int srf_forward_render(srf_stream_t stream, int P, int image_height, int image_w
 
 /* ---- forward, both stages in one call (= srf_forward_preprocess followed by srf_forward_render): what
  * rasterize_gaussians maps to when the caller sizes the binning buffers optimistically.  If the count copied to
- * num_rendered_host exceeds `capacity`, call srf_forward_render again with larger buffers. */
+ * num_rendered_host exceeds `capacity`, call srf_forward_render again with larger buffers.  `count_event` (a
+ * cudaEvent_t, may be NULL) is recorded between the two stages: waiting on it waits for the count, not for the blend. */
 int srf_forward(srf_stream_t stream, int P, int D, int M,
                 const float* means3D, const float* shs, const float* colors_precomp,
                 const float* opacities, const float* scales, float scale_modifier,
@@ -113,7 +114,7 @@ int srf_forward(srf_stream_t stream, int P, int D, int M,
                 float tan_fovx, float tan_fovy, int image_height, int image_width, int prefiltered,
                 const float* background, size_t capacity,
                 int* radii, void* geom_state, void* tile_state, void* entries, uint32_t* point_list, void* image_state,
-                float* out_color, float* out_others, uint32_t* num_rendered_host, int raw_activations);
+                float* out_color, float* out_others, uint32_t* num_rendered_host, void* count_event, int raw_activations);
 
 /* ---- backward ------------------------------------------------------------------
  * Replaces Rasterizer::backward (rasterizer_impl.cu:346-448): BACKWARD::render,

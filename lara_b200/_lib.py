@@ -55,7 +55,7 @@ SIGNATURES = {
         c_int,                              # prefiltered
         _P, c_size_t,                       # background, capacity
         _P, _P, _P, _P, _P, _P,             # radii, geom_state, tile_state, entries, point_list, image_state
-        _P, _P, _P,                         # out_color, out_others, num_rendered_host
+        _P, _P, _P, _P,                     # out_color, out_others, num_rendered_host, count_event
         c_int,                              # raw_activations
     ]),
     "srf_backward": (c_int, [

@@ -513,11 +513,15 @@ int srf_forward(srf_stream_t stream_, int P, int D, int M,
                 float tan_fovx, float tan_fovy, int image_height, int image_width, int prefiltered,
                 const float* background, size_t capacity,
                 int* radii, void* geom_state, void* tile_state, void* entries, uint32_t* point_list, void* image_state,
-                float* out_color, float* out_others, uint32_t* num_rendered_host, int raw_activations) {
+                float* out_color, float* out_others, uint32_t* num_rendered_host, void* count_event, int raw_activations) {
     int rc = srf_forward_preprocess(stream_, P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
                                     transMat_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, image_height,
                                     image_width, prefiltered, radii, geom_state, tile_state, num_rendered_host, raw_activations);
     if (rc != 0) return rc;
+    if (count_event) {      // lets the caller wait for the instance count without waiting for the blend
+        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(count_event), static_cast<cudaStream_t>(stream_));
+        if (e != cudaSuccess) return cuda_fail("count event record", e);
+    }
     return srf_forward_render(stream_, P, image_height, image_width, capacity, geom_state, tile_state, entries, point_list,
                               image_state, background, out_color, out_others);
 }

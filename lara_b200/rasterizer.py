@@ -153,6 +153,7 @@ def _take_readback(device: torch.device, words: int):
     slot = torch.zeros(max(words, _SLOT_WORDS), dtype=torch.int32).pin_memory()
     # blocking (sleeping) wait: the GPU boxes run under a CPU quota, a spinning rank steals cycles from its peers
     ev = torch.cuda.Event(blocking=os.environ.get("SRF_SPIN_EVENT_WAIT", "0") != "1")
+    ev.record()          # materialises the cudaEvent_t so that the C entry point can record it between its two stages
     return slot, ev
 
 
@@ -268,12 +269,14 @@ def _launch_forward(device, lib, nviews, P, capacity, debug, call_pre, call_rend
     slot, ev = rb
     geom, tile, image = state_blobs
     entries, point_list = alloc_binning(capacity)
+    # the event sits between stage 1 (which produces the counts) and stage 2: whoever resolves the counts later waits
+    # for the tile scan, never for the blend
     if call_both is not None:
-        call_both(slot.data_ptr(), capacity, entries, point_list)
+        call_both(slot.data_ptr(), ev.cuda_event, capacity, entries, point_list)
     else:
         call_pre(slot.data_ptr())
+        ev.record()
         call_render(capacity, entries, point_list)
-    ev.record()
     state = ForwardState(geom, tile, image, point_list, capacity, nviews=nviews)
 
     def rerun(new_capacity: int):
@@ -336,7 +339,7 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
     projm = raster_settings.projmatrix
     campos = raster_settings.campos
 
-    def call_both(slot_ptr, capacity, entries, point_list):
+    def call_both(slot_ptr, ev_handle, capacity, entries, point_list):
         _lib.check(lib.srf_forward(
             sptr, P, int(raster_settings.sh_degree), M,
             _ptr(means3D), _ptr(shs), _ptr(colors_precomp),
@@ -346,7 +349,7 @@ def _forward_raw(means3D, shs, colors_precomp, opacities, scales, rotations, tra
             float(raster_settings.tanfovx), float(raster_settings.tanfovy), H, W,
             1 if raster_settings.prefiltered else 0, _ptr(bg), capacity,
             radii.data_ptr(), geom.data_ptr(), tile.data_ptr(), entries.data_ptr(), point_list.data_ptr(), image.data_ptr(),
-            color.data_ptr(), allmap.data_ptr(), slot_ptr, 1 if raw_activations else 0), lib)
+            color.data_ptr(), allmap.data_ptr(), slot_ptr, ev_handle, 1 if raw_activations else 0), lib)
 
     def alloc_binning(capacity):
         ent_b, pl_b = _lib.binning_sizes(lib, capacity)
@@ -428,22 +431,32 @@ def forward_views_raw(means3D, shs, colors_precomp, opacities, scales, rotations
 
 
 def _grad_outputs(P, M, device, shs, colors_precomp, transMat_precomp, out, accumulate, need_means2D):
-    shapes = {"means3D": (P, 3), "means2D": (P, 3) if need_means2D else None,
-              "sh": (P, M, 3) if shs is not None else None,
-              "colors_precomp": (P, 3) if colors_precomp is not None else None,
-              "opacities": (P, 1), "scales": (P, 2), "rotations": (P, 4),
-              "cov3Ds_precomp": (P, 9) if transMat_precomp is not None else None}
-    g = {k: out.get(k) for k in shapes}
-    missing = [k for k, shp in shapes.items() if shp is not None and g[k] is None]
-    if missing:
-        # one allocation for all gradients that the caller did not supply (16-byte aligned segments)
-        sizes = [(-(-int(torch.Size(shapes[k]).numel()) // 4)) * 4 for k in missing]
-        flat = (torch.zeros if accumulate else torch.empty)(sum(sizes), dtype=torch.float32, device=device)
-        o = 0
-        for k, sz in zip(missing, sizes):
-            n = int(torch.Size(shapes[k]).numel())
-            g[k] = flat[o:o + n].view(shapes[k])
-            o += sz
+    """Gradient tensors the caller did not supply: one small allocation each (cheaper on the host than slicing views out
+    of a flat buffer; the caching allocator hands out 512-byte aligned blocks, so the kernel's vector stores are fine)."""
+    new = torch.zeros if accumulate else torch.empty
+    g = {"means3D": out.get("means3D"), "means2D": out.get("means2D"), "sh": out.get("sh"),
+         "colors_precomp": out.get("colors_precomp"), "opacities": out.get("opacities"), "scales": out.get("scales"),
+         "rotations": out.get("rotations"), "cov3Ds_precomp": out.get("cov3Ds_precomp")}
+    if g["means3D"] is None:
+        g["means3D"] = new((P, 3), dtype=torch.float32, device=device)
+    if need_means2D and g["means2D"] is None:
+        g["means2D"] = new((P, 3), dtype=torch.float32, device=device)
+    if shs is not None and g["sh"] is None:
+        g["sh"] = new((P, M, 3), dtype=torch.float32, device=device)
+    if colors_precomp is not None and g["colors_precomp"] is None:
+        g["colors_precomp"] = new((P, 3), dtype=torch.float32, device=device)
+    if g["opacities"] is None:
+        g["opacities"] = new((P, 1), dtype=torch.float32, device=device)
+    if g["scales"] is None:
+        g["scales"] = new((P, 2), dtype=torch.float32, device=device)
+    if g["rotations"] is None:
+        g["rotations"] = new((P, 4), dtype=torch.float32, device=device)
+    if transMat_precomp is not None and g["cov3Ds_precomp"] is None:
+        g["cov3Ds_precomp"] = new((P, 9), dtype=torch.float32, device=device)
+    if not need_means2D:
+        g["means2D"] = out.get("means2D")
+    if shs is None:
+        g["sh"] = None
     return g
 
 
