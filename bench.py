@@ -441,8 +441,16 @@ def main():
     ms, spread = timed_steps(step, args.steps, 0, flush, world, dev)
     value = total_views * args.steps / (ms / 1e3)
     collective_us = None
+    rank_compute_ms = None
     if coll:
         collective_us = 1e3 * sum(a.elapsed_time(b) for a, b in coll[-args.steps:]) / args.steps
+        # per-rank time spent inside the all-reduce (transfer + waiting for the slowest rank), gathered from every rank:
+        # the rank with the SMALLEST value is the one the others wait for
+        mine = torch.tensor([collective_us], dtype=torch.float64, device=dev)
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        rank_compute_ms = [round(ms / args.steps - float(c.item()) / 1e3, 4) for c in allc]   # step time minus own collective time
+        collective_us = {"rank0": collective_us, "per_rank": [round(float(c.item()), 1) for c in allc]}
 
     # ---- hardware correctness of the sharded step: the all-reduced buffer equals the single-rank sum
     grad_check = None
@@ -620,7 +628,7 @@ def main():
             "roofline": roof,
             "kernels_us": {k: (v[0] * 1e3 / v[1] / nv if v[1] else 0.0) for k, v in kern.items()} if kern else None,
             "rank_step_ms": {"min": spread[0] / args.steps, "max": spread[1] / args.steps},
-            "collective_us": collective_us,
+            "collective_us": collective_us, "rank_compute_ms": rank_compute_ms,
             "grad_check": grad_check["status"] if grad_check else None,
             "grad_check_detail": grad_check,
             "extra": extra,

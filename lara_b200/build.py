@@ -8,7 +8,7 @@ source page maps to the .cu files, nvcc's default ``-fmad=true`` and *no*
 intrinsics anyway, see csrc/surfel_common.cuh).
 
     python -m lara_b200.build          # build if sources are newer than the .so
-    python -m lara_b200.build --force
+    python -m lara_b200.build --force [--ptxas-info]     # registers / spills per kernel
 """
 from __future__ import annotations
 
@@ -25,7 +25,7 @@ SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd
 HEADERS = ["surfel_common.cuh", "surfel_kernels.h", os.path.join("..", "..", "include", "surfel_rasterizer.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
 
@@ -43,7 +43,7 @@ def needs_build() -> bool:
     return (not os.path.isfile(LIB)) or os.path.getmtime(LIB) < _newest_source_mtime()
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, ptxas_info: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         if (not force and os.path.isfile(obj)
                 and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_mtime)):
             return obj
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", path, "-o", obj]
         if verbose:
             print("[lara_b200.build]", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
@@ -71,4 +71,4 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, ptxas_info="--ptxas-info" in sys.argv))

@@ -17,11 +17,12 @@
 //   phase 1  lane = pixel.  Every lane walks ITS OWN hits (per-pixel octagon masks, as the forward does)
 //            back to front, does the sequential part and parks (w, GdA, dL/dz) in shared memory
 //            (3 floats per pair, XOR-swizzled so that both phases are bank-conflict free or nearly so).
-//   phase 2  lane = (splat, half block).  Every lane streams the 16 pixels of its half block, rebuilds the
-//            pixel-dependent coefficients from its splat's record held in registers, and accumulates the
-//            18 gradient values in registers -- no cross-lane reduction at all; the two halves are
-//            combined with one shuffle per value and go out as 4 (5) red.global.add.v4.f32 per
-//            (warp, splat).
+//   phase 2  lane = (splat, 0/1).  The two lanes of a splat take its contributing pixels alternately, rebuild the
+//            pixel-dependent coefficients from the splat's record held in registers, and accumulate the 18 gradient
+//            values in registers -- no cross-lane reduction at all; the two lanes are combined with one shuffle per
+//            value and the totals go out as 4 (5) red.global.add.v4.f32 per (warp, splat).
+// Phase 1 evaluates pairs with MUFU.RCP / MUFU.EX2 and re-evaluates with the forward's exact sequence only within a
+// narrow band around the forward's decision thresholds (eval_pair_bwd below).
 // What is kept from round 1: CTA per 16x16 tile in LPT order, the list walked back to front from the tile's
 // deepest used entry in staged rounds, warp-level octagon cull, packed fp32x2 arithmetic, MUFU.RCP.
 #include "surfel_common.cuh"

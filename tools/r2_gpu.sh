@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python tools/profile_view.py --iters 40 --warmup 10 --P 131072
-timeout 300 python tools/profile_view.py --iters 40 --warmup 10 --P 32768
-timeout 300 python tools/profile_view.py --iters 40 --warmup 10 --P 524288
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "
-import json,sys
-d=json.loads([l for l in sys.stdin if l.startswith('{')][-1])
-print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'resident dropin',round(d['e2e']['dropin_api_inputs_resident']['value'],1),'batched e2e',round(d['e2e']['batched']['value'],1))"
+timeout 900 python tools/parity_sweep.py 7 250 > gpurun_out/parity_sweep_r02.log 2>&1; tail -2 gpurun_out/parity_sweep_r02.log
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "cpu_oracle" > gpurun_out/racecheck_r02.txt 2>&1; tail -4 gpurun_out/racecheck_r02.txt
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_views.py tests/test_loss.py tests/test_decoder_layout.py -m gpu -q -x -k "cpu_oracle or 20000 or loss or decoder" > gpurun_out/sanitizer_r02.txt 2>&1; tail -4 gpurun_out/sanitizer_r02.txt
+timeout 600 compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "cpu_oracle" > gpurun_out/synccheck_r02.txt 2>&1; tail -3 gpurun_out/synccheck_r02.txt
