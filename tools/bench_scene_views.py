@@ -3,7 +3,8 @@
    (a) LaRa today: reference rasterizer (oracle/_ref) + torch activations + torch epilogue, per view,
    (b) drop-in rasterizer under the same torch code, per view,
    (c) lara_b200.renderer.Renderer.render_img per view (fused activations + epilogue),
-   (d) Renderer.render_views: one autograd node, multi-stream, in-kernel gradient accumulation."""
+   (d) Renderer.render_views: one autograd node, one launch set for all views, torch loss on the concatenated layout,
+   (e) Renderer.render_views + lara_b200.loss.scene_loss: the fused loss -> gradient-map producer on the stacked buffers."""
 import os, sys, types
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,6 +12,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from lara_b200 import scene as S
 from oracle.torch_restatements import render_img_epilogue_torch
 from lara_b200.multiview import concat_views
+from lara_b200.loss import scene_loss
 from lara_b200.renderer import Renderer
 import diff_surfel_rasterization as DSR
 from oracle import ref as REF
@@ -64,18 +66,25 @@ def batched(streams):
                                                       raw["rotations"], dev, streams=streams))
 
 
+tar_views = tar.view(H, V, W, 3).permute(1, 0, 2, 3).contiguous()          # the batch's own [V,H,W,3] layout
+
+
+def fused_loss_step(raw):
+    out = fast.render_views(cams, rays, raw["centers"], raw["shs"], raw["opacity"], raw["scales"], raw["rotations"], dev)
+    return scene_loss(out, tar_views, 5000)[0]
+
+
 variants = [("LaRa today: reference rasterizer, torch activations + epilogue, per-view loop", torch_loop(ref)),
             ("drop-in B200 rasterizer under the same torch code", torch_loop(DSR)),
             ("Renderer.render_img per view (fused activations + epilogue)", fast_loop),
-            ("Renderer.render_views, 1 stream", batched(1)),
-            ("Renderer.render_views, 3 streams", batched(3)),
-            ("Renderer.render_views, 4 streams", batched(4))]
+            ("Renderer.render_views (one launch set), torch loss on the concatenated layout", batched(1)),
+            ("Renderer.render_views + fused scene_loss (no concat, one loss kernel each way)", None)]
 for name, fn in variants:
     raw = {k: v.clone().requires_grad_(True) for k, v in base.items()}
     def step():
         for v in raw.values():
             v.grad = None
-        loss_of(fn(raw)).backward()
+        (fused_loss_step(raw) if fn is None else loss_of(fn(raw))).backward()
     for _ in range(3):
         step()
     torch.cuda.synchronize()

@@ -107,5 +107,14 @@ w(f"`roofline` in the bench line is computed as specified: SURVEY 8d algorithmic
   ".  Round 1 → round 2: 308 M → 231 M warp instructions per view in the backward (two-phase kernel), 128 M → 118 M in the forward (cull + compaction before the masks).  "
   "By the same §8(d) accounting the streaming kernels sit at: K1 0.28, binning (scan + scatter + sorts) 0.90, K8+K9 1.27 of the measured HBM roof "
   "(DESIGN.md §3 table); K1 is latency-bound on its per-tile counting atomics (ncu: long-scoreboard stalls 12 per issue).\n")
+sv = os.path.join(P, "scene_views_r02.log")
+if os.path.isfile(sv):
+    w("## One scene-step of the renderer: 8 target views of one Gaussian set + loss + backward, 512×512 (`tools/bench_scene_views.py`)\n")
+    w("The loop of `lightning/network.py:486-495`, the cat of `:525`, the `loss.py` terms (MSE + 1000·distortion + 0.2·normal consistency), `loss.backward()`:\n")
+    w("```")
+    for line in open(sv):
+        if line.startswith("P="):
+            w(line.rstrip()[:170])
+    w("```\n")
 open(os.path.join(P, "README.md"), "w").write("\n".join(o) + "\n")
 print("\n".join(o)[:3000])

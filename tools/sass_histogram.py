@@ -14,11 +14,13 @@ for line in out.split("\n"):
         arch.add(m.group(1))
     m = re.search(r"Function : (\S+)", line)
     if m:
-        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
-        kern = kern.replace("void ", "").replace("srf::", "").replace("(anonymous namespace)::", "")
+        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = kern.replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        kern = re.sub(r"\((srf::)?\w*Args\)$|\(int, float const\*, float const\*, unsigned char\*\)$", "", kern).replace("srf::", "")
+        kern = kern.replace("(int)", "").replace("(bool)", "")
         hist[kern] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Za-z0-9_.]*)", line)
     if m and kern:
         hist[kern][m.group(1)] += 1
 WATCH = ["FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "MUFU.RCP", "MUFU.EX2", "MUFU.RSQ", "MUFU.SQRT", "MUFU.LG2", "DFMA", "DMUL",
