@@ -72,6 +72,7 @@ for n, b in ((1, b1), (2, b2), (4, b4), (8, b8)):
     w(f"| {n} | {b['value']:.0f} | {b['value']/(n*b1['value']):.3f} | {b['e2e']['value']:.0f} | {b['e2e']['batched']['value']:.0f} | "
       f"{((b.get('collective_us') or {}).get('rank0', 0) if isinstance(b.get('collective_us'), dict) else (b.get('collective_us') or 0)):.0f} | {gc.get('status', '—')} {('(%.1e)' % gc['max_rel_err']) if gc else ''} | {st.get('value', 0):.0f} ({st.get('ms_per_step', 0):.2f} ms/step) |")
 w("")
+w("The first 4-GPU run of the final tree measured 7494 views/s (0.930) with rank 2 about 7 % behind the others in `rank_compute_ms` (`bench_r02_n4_run1.json`); the rerun on a fresh box is the row above — the difference is the box, not the code.\n")
 w("The pure all-reduce takes ~100–120 µs on 8 GPUs (`allreduce_probe_n8.log`, ranks in lock-step); the rest of `collective_us` in the "
   "bench is ranks waiting for the slowest one.  Reference at 8 GPUs: it is single-GPU, so 8×B200 vs 1×B200 is "
   f"{(b8['value']/rv if b8 else 0):.1f}× (`value`) / {(b8['e2e']['value']/rv if b8 else 0):.1f}× (`e2e`).\n")
