@@ -114,6 +114,7 @@ SIGNATURES = {
     "srf_epilogue_backward": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srf_profile_begin": (c_int, []),
     "srf_profile_end": (c_int, [POINTER(c_float), POINTER(c_int), c_int]),
+    "srf_select_bwd_variant": (c_int, [c_int]),
 }
 
 _lib = None
@@ -187,6 +188,11 @@ def layout(lib, P: int, H: int, W: int):
 
 KERNEL_NAMES = ["preprocess_fwd", "tile_scan", "scatter", "sort_small", "sort_big", "render_fwd",
                 "render_bwd", "preprocess_bwd"]
+
+
+def select_bwd_variant(variant: int, lib=None) -> int:
+    """Tools only: A/B selection of the blend-backward kernel variant; returns the previous one."""
+    return int((lib or load()).srf_select_bwd_variant(int(variant)))
 
 
 def profile_begin(lib=None) -> None:

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -112,12 +113,17 @@ void prof_stop(int kernel, cudaStream_t stream) {
     g_spans.push_back(s);
 }
 
+// blend-backward kernel selection: SRF_BWD_VARIANT (read once) or srf_select_bwd_variant() (tools: A/B in one process)
+constexpr int kBwdVariantDefault = 17, kBwdVariantMax = 18;
+static std::atomic<int> g_bwd_variant{0};
 int bwd_variant() {
-    static const int v = [] {
+    int v = g_bwd_variant.load(std::memory_order_relaxed);
+    if (v == 0) {
         const char* e = getenv("SRF_BWD_VARIANT");
-        const int x = e ? atoi(e) : 7;
-        return (x >= 1 && x <= 8) ? x : 7;
-    }();
+        const int x = e ? atoi(e) : kBwdVariantDefault;
+        v = (x >= 1 && x <= kBwdVariantMax) ? x : kBwdVariantDefault;
+        g_bwd_variant.store(v, std::memory_order_relaxed);
+    }
     return v;
 }
 
@@ -138,6 +144,12 @@ int sm_count() {
 extern "C" {
 
 int srf_abi_version(void) { return SRF_ABI_VERSION; }
+
+int srf_select_bwd_variant(int variant) {
+    const int prev = srf::bwd_variant();
+    if (variant >= 1 && variant <= srf::kBwdVariantMax) srf::g_bwd_variant.store(variant, std::memory_order_relaxed);
+    return prev;
+}
 
 int srf_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

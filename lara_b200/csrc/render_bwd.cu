@@ -48,6 +48,21 @@ __device__ __forceinline__ f32x2 shfl_xor2(f32x2 v, int m) {
     return (f32x2)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, m);
 }
 
+// explicit 32-bit shared-memory addressing for the phase-1 loop (SADDR): with pointer-typed accesses the compiler
+// rebuilds the shared window base (S2R SR_CgaCtaId + LEA) inside the loop, in front of the first dependent load
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 __device__ __forceinline__ float ex2_fast(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -119,10 +134,13 @@ struct BwdSmem {
 // EXACT : phase 1 evaluates pairs with the forward's exact sequence (else approximate + exact re-check at thresholds)
 // P2WALK: 0 = all phase-2 lanes step through the 16 pixels of their half block together; 1 = every lane walks the
 //         contributing pixels of its own half block; 2 = the two lanes of a splat share ALL its contributing pixels
-//         alternately (a splat that only touches one half block no longer leaves its other lane idle)
+//         alternately (a splat that only touches one half block no longer leaves its other lane idle); 3 = the 32
+//         lanes are allotted to the group's splats in proportion to their contributing pixels (see phase 2 below)
 // SMEMC : phase 1 reads the pixel's upstream gradients from shared memory (eight registers less)
 // NW    : warps per CTA -- 8 = one CTA per 16x16 tile, 4 = one CTA per 16x8 half tile (two CTAs walk the tile's list)
-template <int BATCH, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC>
+// PREF  : (BATCH == threads) every thread fetches the list entry it will stage in the NEXT round while the current
+//         round is being processed, so that a round's staging waits for one global load, not two dependent ones
+template <int BATCH, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC, bool PREF = false, bool SADDR = false, bool PIXREG = false>
 __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs a) {
     static_assert(BATCH <= 256, "hit lists are uint8");
     extern __shared__ __align__(16) unsigned char smem[];
@@ -136,6 +154,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* s_xw = reinterpret_cast<float*>(smem + L::x) + wid * (3 * kBwdGroup * 32);
     uint8_t* s_listw = reinterpret_cast<uint8_t*>(smem + L::list) + wid * BATCH;
+    uint32_t sa_base = SADDR ? smem_addr(smem) : 0u;
+    if (SADDR) asm volatile("" : "+r"(sa_base));          // opaque: kept in a register, not rebuilt at every use
+    const uint32_t sa_rec = sa_base + (uint32_t)L::rec, sa_x = sa_base + (uint32_t)(L::x + wid * (3 * kBwdGroup * 32 * sizeof(float))),
+                   sa_list = sa_base + (uint32_t)(L::list + wid * BATCH);
 
     const int view = blockIdx.y;
     const size_t npix = (size_t)a.W * a.H;
@@ -213,8 +235,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
     float last_dL_dT = 0.f;
     const float nTfinal_bg = -T_final * bg_dot_dpixel;
 
+    // this lane's pixel centre (PIXREG: held in two registers instead of being rebuilt from the lane id per pair)
+    float pixx = bx0 + (float)(lane & 7), pixy = by0 + (float)(lane >> 3);
+    if (PIXREG) asm volatile("" : "+f"(pixx), "+f"(pixy));
+
     // phase-2 identity of this lane
     const int p2_i = lane & (kBwdGroup - 1), p2_h = lane >> 4;
+    // P2WALK 3: this lane's candidate chunk size C = p2_i + 1 and the multiplier that turns n / C into a multiply
+    // ((n * M) >> 16 == n / C exactly while n * C < 65536; n <= 47, C <= 16 here)
+    const uint32_t candM = 65536u / (uint32_t)(p2_i + 1) + 1u;
+
+    static_assert(!PREF || BATCH == NW * 32, "PREF stages one entry per thread and round");
+    uint32_t next_id = 0;
+    if (PREF && n_eff - 1 - tid >= 0) next_id = __ldg(a.point_list + range.x + (n_eff - 1 - tid));
 
     for (int b = 0; b < rounds; ++b) {
         // ---- stage batch b (back to front: slot j holds list position n_eff-1-(b*BATCH+j))
@@ -222,13 +255,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
         for (int jt = tid; jt < BATCH; jt += NT) {
             const int pos = n_eff - 1 - (b * BATCH + jt);
             if (pos >= 0) {
-                const uint32_t id = __ldg(a.point_list + range.x + pos);
+                const uint32_t id = PREF ? next_id : __ldg(a.point_list + range.x + pos);
                 const float4* r = a.rec + (size_t)id * SRF_REC_QUADS;
 #pragma unroll
                 for (int k = 0; k < SRF_REC_QUADS; ++k) s_rec[k][jt] = ldg4(r + k);
                 // the splat id rides in the (otherwise unused by the blend) clamp-bits word of q4
                 s_rec[4][jt].w = __uint_as_float(id);
             }
+        }
+        if (PREF) {
+            const int npos = n_eff - 1 - ((b + 1) * BATCH + tid);
+            if (npos >= 0) next_id = __ldg(a.point_list + range.x + npos);
         }
         __syncthreads();
         const int cnt = min(BATCH, n_eff - b * BATCH);
@@ -273,15 +310,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                     if (bits == 0) continue;
                     const int i = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    const int j = lst[i];
+                    const int j = SADDR ? (int)lds_u8(sa_list + gbase + i) : (int)lst[i];
                     const int pos = n_eff - 1 - (b * BATCH + j);   // 0-based position in the tile list
                     if (pos >= last_contributor) continue;
                     PairBwd e;
-                    eval_pair_bwd<EXACT>(s_rec[0][j], s_rec[1][j], s_rec[2][j], bx0 + (float)(lane & 7), by0 + (float)(lane >> 3), e);
+                    const uint32_t sa_j = sa_rec + 16u * j;
+                    if (SADDR)
+                        eval_pair_bwd<EXACT>(lds_f4(sa_j), lds_f4(sa_j + 16u * BATCH), lds_f4(sa_j + 32u * BATCH), pixx, pixy, e);
+                    else
+                        eval_pair_bwd<EXACT>(s_rec[0][j], s_rec[1][j], s_rec[2][j], pixx, pixy, e);
                     if (!e.valid) continue;
                     const bool lowpass = e.lowpass;
-                    const float4 q3 = s_rec[3][j];
-                    const float4 q4 = s_rec[4][j];
+                    const float4 q3 = SADDR ? lds_f4(sa_j + 48u * BATCH) : s_rec[3][j];
+                    const float4 q4 = SADDR ? lds_f4(sa_j + 64u * BATCH) : s_rec[4][j];
                     const float alpha = e.alpha, c_d = e.depth;
 
                     // one reciprocal serves T / (1-alpha) and the background term's T_final / (1-alpha)
@@ -330,10 +371,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                     dL_dalpha = fmaf(nTfinal_bg, r1ma, dL_dalpha);
 
                     // park the three scalars phase 2 needs; the sign of w carries the branch (w > 0 always)
-                    float* xp = s_xw + (i * 32 + (lane ^ i));
-                    xp[0] = lowpass ? -w : w;
-                    xp[kBwdGroup * 32] = e.G * dL_dalpha;
-                    xp[2 * kBwdGroup * 32] = dL_dz;
+                    if (SADDR) {
+                        const uint32_t xa = sa_x + 4u * (uint32_t)(i * 32 + (lane ^ i));
+                        sts_f(xa, lowpass ? -w : w);
+                        sts_f(xa + 4u * kBwdGroup * 32, e.G * dL_dalpha);
+                        sts_f(xa + 8u * kBwdGroup * 32, dL_dz);
+                    } else {
+                        float* xp = s_xw + (i * 32 + (lane ^ i));
+                        xp[0] = lowpass ? -w : w;
+                        xp[kBwdGroup * 32] = e.G * dL_dalpha;
+                        xp[2 * kBwdGroup * 32] = dL_dz;
+                    }
                     vbits |= 1u << i;
                 }
 
@@ -342,18 +390,73 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                 // ================= phase 2: lane = (splat i, half block h) =================
                 // valid-pair words: lane i (< 16) receives "which pixels contributed to splat i"
                 const uint32_t tw = transpose32(vbits, lane);
-                const uint32_t word = __shfl_sync(0xffffffffu, tw, p2_i);
-                const bool have = gbase + p2_i < nh;
-                uint32_t mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
-                if (P2WALK == 2) {
-                    mybits = have ? word : 0u;
-                    if (p2_h) mybits &= mybits - 1;        // the second lane of a splat starts at its second pixel
+                int own = p2_i;               // the splat of the group this lane accumulates for
+                uint32_t word, mybits, tmask = 0u;
+                bool have;
+                int iters2;
+                if (P2WALK == 3) {
+                    // Lanes in proportion to work.  Splat i has c_i contributing pixels; with chunk size C it gets
+                    // n_i = ceil(c_i / C) lanes, lane r of them takes its pixels of rank [r C, (r + 1) C), and the loop
+                    // below makes C trips.  C is the smallest value for which the lanes suffice (sum n_i <= 32;
+                    // C = 16 always does): ~8.5 trips per group on the bench scene against ~15 with two lanes per
+                    // splat (tools/phase2_balance.py).
+                    const int cnt = __popc(tw);                    // lanes >= 16 hold no word: 0
+                    if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
+                    // lane (C - 1) + 16 h adds up ceil(c_i / C) over the splats 8 h .. 8 h + 7
+                    int part = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int c = __shfl_sync(0xffffffffu, cnt, p2_h * 8 + k);
+                        part += (int)(((uint32_t)(c + p2_i) * candM) >> 16);
+                    }
+                    const int lanes_needed = part + __shfl_xor_sync(0xffffffffu, part, 16);
+                    const int C = __ffs(__ballot_sync(0xffffffffu, lanes_needed <= 32) & 0xffffu);      // 1..16
+                    const uint32_t M = __shfl_sync(0xffffffffu, candM, C - 1);
+                    const int n_mine = (int)(((uint32_t)(cnt + C - 1) * M) >> 16);                       // lanes >= 16: 0
+                    int end = n_mine;                              // inclusive scan over the lanes 0..15
+#pragma unroll
+                    for (int o = 1; o < kBwdGroup; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, end, o);
+                        if (lane >= o) end += v;
+                    }
+                    const int lanes_used = __shfl_sync(0xffffffffu, end, kBwdGroup - 1);
+                    // owner of this lane: the first splat whose lanes end beyond it (lower bound over end[0..15])
+                    own = 0;
+#pragma unroll
+                    for (int st = kBwdGroup / 2; st > 0; st >>= 1) {
+                        const int e = __shfl_sync(0xffffffffu, end, own + st - 1);
+                        if (e <= lane) own += st;
+                    }
+                    const int own_end = __shfl_sync(0xffffffffu, end, own);
+                    const int own_n = __shfl_sync(0xffffffffu, n_mine, own);
+                    word = __shfl_sync(0xffffffffu, tw, own);
+                    have = lane < lanes_used;
+                    // drop the lowest r C contributing pixels of the word (r = rank of this lane among the splat's
+                    // lanes; r C < c_own): the largest pos with popc(word below pos) <= r C
+                    const int skip = (lane - (own_end - own_n)) * C;
+                    int pos = 0;
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1) {
+                        const int below = __popc(word & ((1u << (pos + st)) - 1u));
+                        if (below <= skip) pos += st;
+                    }
+                    mybits = have ? (word & (0xffffffffu << pos)) : 0u;
+                    if (!have) { own = 0; word = 0u; }
+                    iters2 = C;
+                } else {
+                    word = __shfl_sync(0xffffffffu, tw, p2_i);
+                    have = gbase + p2_i < nh;
+                    mybits = have ? ((word >> (16 * p2_h)) & 0xffffu) : 0u;
+                    if (P2WALK == 2) {
+                        mybits = have ? word : 0u;
+                        if (p2_h) mybits &= mybits - 1;        // the second lane of a splat starts at its second pixel
+                    }
+                    tmask = __reduce_or_sync(0xffffffffu, mybits);
+                    iters2 = P2WALK == 2 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mybits) + 1) >> 1)
+                           : P2WALK == 1 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(mybits)) : __popc(tmask);
                 }
-                uint32_t tmask = __reduce_or_sync(0xffffffffu, mybits);
-                const int iters2 = P2WALK == 2 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)(__popc(mybits) + 1) >> 1)
-                                 : P2WALK == 1 ? (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(mybits)) : __popc(tmask);
                 if (iters2 == 0) continue;
-                const int j2 = have ? (int)lst[p2_i] : 0;
+                const int j2 = have ? (int)lst[own] : 0;
                 const float4 q0 = s_rec[0][j2], q1 = s_rec[1][j2], q2 = s_rec[2][j2];
                 const uint32_t splat_id = __float_as_uint(s_rec[4][j2].w);
                 const f32x2 nTu_x = pk2(-q0.x, -q0.y), nTu_y = pk2(-q0.z, -q0.w), nTu_z = pk2(-q1.x, -q1.y);
@@ -363,9 +466,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                 // accumulators, laid out as the gradient record: (DT0,DT1) (DT2,DT3) (DT4,DT5) (DT6,DT7) (DT8,DOPAC)
                 // (DN0,DN1) (DN2,DC0) (DC1,DC2) (DM0,DM1)
                 f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull, A3 = 0ull, A4 = 0ull, A5 = 0ull, A6 = 0ull, A7 = 0ull, A8 = 0ull;
-                const float* xrow = s_xw + p2_i * 32;
-                const float ybase = by0 + (P2WALK == 2 ? 0.0f : (float)(2 * p2_h));
-                const int pbase = wid * 32 + (P2WALK == 2 ? 0 : 16 * p2_h);
+                const float* xrow = s_xw + own * 32;
+                const float ybase = by0 + (P2WALK >= 2 ? 0.0f : (float)(2 * p2_h));
+                const int pbase = wid * 32 + (P2WALK >= 2 ? 0 : 16 * p2_h);
 #pragma unroll 1
                 for (int it = 0; it < iters2; ++it) {
                     int t;
@@ -374,7 +477,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                         t = __ffs(mybits) - 1;             // mine ...
                         mybits &= mybits - 1;
                         mybits &= mybits - 1;              // ... and the next one is the partner lane's
-                    } else if (P2WALK == 1) {
+                    } else if (P2WALK == 1 || P2WALK == 3) {
                         if (mybits == 0) continue;
                         t = __ffs(mybits) - 1;             // every lane walks its own contributing pixels
                         mybits &= mybits - 1;
@@ -383,9 +486,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                         tmask &= tmask - 1;
                         if (!((mybits >> t) & 1u)) continue;
                     }
-                    const int p = P2WALK == 2 ? t : t + 16 * p2_h;
+                    const int p = P2WALK >= 2 ? t : t + 16 * p2_h;
                     const float ppx = bx0 + (float)(t & 7), ppy = ybase + (float)(t >> 3);
-                    const float* xp = xrow + (p ^ p2_i);
+                    const float* xp = xrow + (p ^ own);
                     const float ws = xp[0], GdA = xp[kBwdGroup * 32], dL_dz = xp[2 * kBwdGroup * 32];
                     const float4 pa = s_pixA[pbase + t];
                     const float4 pb = s_pixB[pbase + t];
@@ -431,6 +534,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                         add2_acc(A4, pk2(dL_dz, GdA));
                     }
                 }
+                if (P2WALK == 3) {
+                    // every lane sends its own partial sums (a lane that is in use took at least one pair)
+                    if (have) {
+                        float* dst = a.ggrad + (size_t)splat_id * SRF_GRAD_FLOATS;
+                        const float2 a0 = up2(A0), a1 = up2(A1), a2 = up2(A2), a3 = up2(A3), a8 = up2(A8);
+                        const float2 a4 = up2(A4), a5 = up2(A5), a6 = up2(A6), a7 = up2(A7);
+                        red_add_v4(dst + 0, a0.x, a0.y, a1.x, a1.y);
+                        red_add_v4(dst + 4, a2.x, a2.y, a3.x, a3.y);
+                        red_add_v4(dst + 8, a4.x, a4.y, a5.x, a5.y);
+                        red_add_v4(dst + 12, a6.x, a6.y, a7.x, a7.y);
+                        if (a8.x != 0.0f || a8.y != 0.0f) red_add_v4(dst + 16, a8.x, a8.y, 0.0f, 0.0f);
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 // combine the two half blocks and send the totals out: lanes of half 0 own record quads 0,1
                 // (and 4 if a low-pass pair touched the splat), lanes of half 1 own quads 2,3
                 A0 = add2(A0, shfl_xor2(A0, 16)); A1 = add2(A1, shfl_xor2(A1, 16));
@@ -461,9 +579,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
 
 cudaError_t launch_render_bwd_v1(const RenderBwdArgs& a, cudaStream_t stream);
 
-template <int B, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC>
+template <int B, int NW, int MINB, bool EXACT, int P2WALK, bool SMEMC, bool PREF = false, bool SADDR = false, bool PIXREG = false>
 static cudaError_t launch_variant(const RenderBwdArgs& a, cudaStream_t stream) {
-    auto k = render_bwd_kernel<B, NW, MINB, EXACT, P2WALK, SMEMC>;
+    auto k = render_bwd_kernel<B, NW, MINB, EXACT, P2WALK, SMEMC, PREF, SADDR, PIXREG>;
     // the opt-in is per device (and cheap): made on every call for the current device
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<B, NW>::total);
     if (e != cudaSuccess) return e;
@@ -485,6 +603,16 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
         case 6: e = launch_variant<256, 4, 4, false, 1, false>(a, stream); break;      // half-tile CTAs
         case 2: e = launch_variant<256, 8, 2, false, 1, false>(a, stream); break;      // one CTA per tile, own-half phase-2 lanes
         case 8: e = launch_variant<256, 8, 2, false, 2, false>(a, stream); break;      // one CTA per tile, shared phase-2 lanes
+        case 9: e = launch_variant<256, 4, 4, false, 3, false>(a, stream); break;      // half-tile CTAs, phase-2 lanes in proportion to work
+        case 10: e = launch_variant<256, 8, 2, false, 3, false>(a, stream); break;     // one CTA per tile, the same
+        case 11: e = launch_variant<128, 4, 5, false, 3, true>(a, stream); break;      // five half-tile CTAs per SM (<= 102 registers)
+        case 12: e = launch_variant<128, 4, 5, false, 3, false>(a, stream); break;
+        case 13: e = launch_variant<64, 4, 6, false, 3, true>(a, stream); break;
+        case 14: e = launch_variant<128, 8, 3, false, 3, true>(a, stream); break;
+        case 15: e = launch_variant<128, 4, 5, false, 2, false>(a, stream); break;
+        case 16: e = launch_variant<128, 4, 5, false, 3, false, true>(a, stream); break;
+        case 17: e = launch_variant<128, 4, 5, false, 3, false, true, true>(a, stream); break;
+        case 18: e = launch_variant<128, 4, 5, false, 3, false, true, true, true>(a, stream); break;
         default: e = launch_variant<256, 4, 4, false, 2, false>(a, stream); break;     // 7: half-tile CTAs, shared phase-2 lanes
     }
     prof_stop(K_RENDER_BWD, stream);
