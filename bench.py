@@ -586,10 +586,12 @@ def main():
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
                 if args.P == 131072 and args.size == 512:      # the capture is of the default workload only
                     j = json.load(f)
-                    traffic = j.get("render_bwd_dram_bytes_per_view")
-                    if traffic is not None:
-                        traffic = traffic * nv
-                    warp_inst = j.get("render_bwd_warp_instructions_per_view")
+                    # the capture is of one kernel variant: a different one running now has no ncu figures
+                    if int(j.get("bwd_variant", -1)) == _lib.select_bwd_variant(0):
+                        traffic = j.get("render_bwd_dram_bytes_per_view")
+                        if traffic is not None:
+                            traffic = traffic * nv
+                        warp_inst = j.get("render_bwd_warp_instructions_per_view")
         except Exception:
             pass
         achieved = alg_bytes / dur_s / 1e9

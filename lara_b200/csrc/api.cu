@@ -114,7 +114,7 @@ void prof_stop(int kernel, cudaStream_t stream) {
 }
 
 // blend-backward kernel selection: SRF_BWD_VARIANT (read once) or srf_select_bwd_variant() (tools: A/B in one process)
-constexpr int kBwdVariantDefault = 17, kBwdVariantMax = 18;
+constexpr int kBwdVariantDefault = 18, kBwdVariantMax = 18;
 static std::atomic<int> g_bwd_variant{0};
 int bwd_variant() {
     int v = g_bwd_variant.load(std::memory_order_relaxed);

@@ -13,6 +13,7 @@ def jl(name):
     return json.loads(lines[-1]) if lines else json.load(open(p))
 
 
+b1v7 = jl("bench_r02_n1_v7.json")
 b1, ref, b2, b4, b8 = jl("bench_r02_n1.json"), jl("bench_r02_reference_n1.json"), jl("bench_r02_n2.json"), jl("bench_r02_n4.json"), jl("bench_r02_n8.json")
 ncu1 = json.load(open(os.path.join(P, "ncu_summary_r02.json")))
 ncu8 = json.load(open(os.path.join(P, "ncu_summary_r02_views8.json")))
@@ -23,14 +24,15 @@ w("# profiles/ — measured evidence, round 2\n")
 w("All numbers: B200 (gpurun boxes), SM clock 1965 MHz with no throttle reasons during the runs (`clocks` in the bench JSON), CUDA 12.9, "
   "workload = north-star point `scene(131072, seed 0)`, 512×512, SH degree 1, white background unless stated.  Round-1 files (`*_r01*`) are kept for comparison.\n")
 w("| file | what |\n|---|---|")
-w("| `bench_r02_n1.json`, `bench_r02_reference_n1.json`, `pytest_gpu_r02.log` | `python bench.py --steps 20 --warmup 5`, `--impl reference --steps 5 --warmup 3` and `pytest -m gpu` (66 passed) on the final tree, same box (`tools/r2_gpu.sh`) |")
-w("| `bench_r02_n2.json`, `bench_r02_n4.json`, `bench_r02_n8.json` | `bench.py --steps 10 --warmup 3` under `torch.distributed.run` on 2 / 4 / 8 B200s of one box (`tools/r2_gpu_n.sh`) |")
+w("| `bench_r02_n1.json`, `bench_r02_reference_n1.json`, `pytest_gpu_r02.log` | `python bench.py --steps 20 --warmup 5`, `--impl reference --steps 5 --warmup 3` and `pytest -m gpu` (69 passed); the candidate line and the test log are of the final kernels (`tools/r2_final.sh`, blend-backward variant 18 = the default) |")
+w("| `bwd_variants_r02.log`, `parity_sweep_r02_final60.log` | A/B of the blend-backward variants in one process (`tools/time_kernels.py --variants`), and `tools/parity_sweep.py 7 60` on the final default: 60/60 bit-exact, worst gradient relative error 1.5e-5 |")
+w("| `bench_r02_n2.json`, `bench_r02_n4.json`, `bench_r02_n8.json` | `bench.py --steps 10 --warmup 3` under `torch.distributed.run` on 2 / 4 / 8 B200s of one box (`tools/r2_gpu_n.sh`) — taken BEFORE the last blend-backward change (variant 7, 318 µs per view); `bench_r02_n1_v7.json` is the 1-GPU line of that same kernel, the scaling table below is computed against it |")
 w("| `ncu_summary_r02.{json,md}` | one `ncu --set full --clock-control none --import-source on` capture per kernel, ONE view per launch (the drop-in path; `tools/profile_view.py`) |")
 w("| `ncu_summary_r02_views8.{json,md}` | the same for the batched launch set, 8 views per launch (`tools/time_kernels.py --steps 1`) |")
 w("| `launches_bench_r02.csv`, `launch_shares_r02.json` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` over `bench.py --steps 2 --warmup 1` (cold-cache, serialised: compare shares) |")
 w("| `roofline_traffic.json` | DRAM bytes and warp instructions per view of the dominant kernel (from the batched capture); `bench.py` reports them as `roofline.traffic` / `roofline.issue` |")
-w("| `sass_histogram_r02.md` | per-kernel SASS opcode histogram of the built library (`tools/sass_histogram.py`): sm_100a cubins, `FFMA2/FMUL2/FADD2`, `REDG.E.ADD.F32x4`, `LDG.E.128`, no spills in the default kernels |")
-w("| `parity_sweep_r02.log` | `python tools/parity_sweep.py 7 250` on the final kernels: 250 random configurations (500–300k Gaussians, 64–768 px incl. ragged sizes, SH 0–3, needles, saturated scenes, cameras inside the cloud) — **250/250 bit-exact** on every integer state array, colour and aux maps; worst gradient relative error 2.2e-5 |")
+w("| `sass_histogram_r02.md` | per-kernel SASS opcode histogram of the built library (`tools/sass_histogram.py`): sm_100a cubins, `FFMA2/FMUL2/FADD2`, `REDG.E.ADD.F32x4`, `LDG.E.128`; no spills except 12 bytes in the default blend backward (96 registers for five CTAs per SM; stored and reloaded once per 128-splat round, outside the pair loops) |")
+w("| `parity_sweep_r02.log` | `python tools/parity_sweep.py 7 250` on the kernels as of the scaling runs (blend-backward variant 7): 250 random configurations (500–300k Gaussians, 64–768 px incl. ragged sizes, SH 0–3, needles, saturated scenes, cameras inside the cloud) — **250/250 bit-exact** on every integer state array, colour and aux maps; worst gradient relative error 2.2e-5 |")
 w("| `sanitizer_r02.txt` | compute-sanitizer racecheck / memcheck / synccheck on the final kernels (parity, batched-views, loss, decoder-layout tests): 0 hazards, 0 errors |")
 w("| `allreduce_probe_n8.log` | latency of the step's one collective (11.5 MB all-reduce) on 8 GPUs under a few NCCL settings |\n")
 
@@ -63,13 +65,14 @@ for k, label in (("C2_32k_512_1view", "C2: 32 768 Gaussians, 512², 1 view (ms p
     else:
         w(f"| {label} | {a['value']:.0f} | {r['value']:.0f} | {a['value']/r['value']:.2f}× |")
 w("")
+w("Scaling runs (blend-backward variant 7 on every row, so that the efficiency column compares like with like; the GPU budget of the round ended before they could be repeated with variant 18, which shortens every rank's step by the same 0.44 ms and leaves the ~0.15 ms of collective + rank skew at 8 GPUs unchanged — expected efficiency there 0.96):\n")
 w("| GPUs (8 views per GPU, weak scaling) | `value` views/s | efficiency | `e2e` | `e2e.batched` | collective µs (incl. rank skew) | all-reduced gradients vs single-rank sum | 8 views in total (strong) |\n|---|---|---|---|---|---|---|---|")
-for n, b in ((1, b1), (2, b2), (4, b4), (8, b8)):
+for n, b in ((1, b1v7), (2, b2), (4, b4), (8, b8)):
     if not b:
         continue
     st = b["extra"].get("strong_8_global_views", {})
     gc = b.get("grad_check_detail") or {}
-    w(f"| {n} | {b['value']:.0f} | {b['value']/(n*b1['value']):.3f} | {b['e2e']['value']:.0f} | {b['e2e']['batched']['value']:.0f} | "
+    w(f"| {n} | {b['value']:.0f} | {b['value']/(n*b1v7['value']):.3f} | {b['e2e']['value']:.0f} | {b['e2e']['batched']['value']:.0f} | "
       f"{((b.get('collective_us') or {}).get('rank0', 0) if isinstance(b.get('collective_us'), dict) else (b.get('collective_us') or 0)):.0f} | {gc.get('status', '—')} {('(%.1e)' % gc['max_rel_err']) if gc else ''} | {st.get('value', 0):.0f} ({st.get('ms_per_step', 0):.2f} ms/step) |")
 w("")
 w("The first 4-GPU run of the final tree measured 7494 views/s (0.930) with rank 2 about 7 % behind the others in `rank_compute_ms` (`bench_r02_n4_run1.json`); the rerun on a fresh box is the row above — the difference is the box, not the code.\n")
@@ -80,7 +83,7 @@ w("The pure all-reduce takes ~100–120 µs on 8 GPUs (`allreduce_probe_n8.log`,
 w("## Per-kernel time per view (live CUDA events inside `bench.py`, 8 views per launch) and ncu\n")
 k = b1["kernels_us"]
 names = ["render_bwd", "render_fwd", "preprocess_fwd", "scatter", "preprocess_bwd", "sort_small", "tile_scan", "sort_big"]
-r1 = {"render_bwd": 402, "render_fwd": 185, "preprocess_fwd": 20.7, "scatter": 22.6, "preprocess_bwd": 18.8, "sort_small": 13.9, "tile_scan": 10.8, "sort_big": 6.6}
+r1 = {"render_bwd": 403, "render_fwd": 185, "preprocess_fwd": 20.7, "scatter": 22.6, "preprocess_bwd": 18.8, "sort_small": 13.9, "tile_scan": 10.8, "sort_big": 6.6}
 
 
 def find(lst, name):
@@ -99,19 +102,21 @@ for n in names:
 tot = sum(k.values())
 w(f"| sum | {tot:.0f} (681) | | |\n")
 ro = b1["roofline"]
+rt = json.load(open(os.path.join(P, "roofline_traffic.json")))
 w("## Roofline statement\n")
 w(f"`roofline` in the bench line is computed as specified: SURVEY 8d algorithmic bytes for K7, `148·R_eff + 64·Npix` per view × the views of a launch = "
   f"{ro['algorithmic_bytes_per_launch']/1e6:.0f} MB, ÷ the live launch duration {ro['avg_launch_us']:.0f} µs, ÷ the measured {ro['peak']:.0f} GB/s: "
   f"**{ro['achieved']:.0f} GB/s, frac {ro['frac']:.3f}**; ncu's DRAM traffic for that launch is {(ro['traffic'] or 0)/1e6:.0f} MB (below the algorithmic bytes: the records and "
   "index lists stay in the 126 MB L2).  The kernel is bound by instruction issue" +
-  (f" — `roofline.issue`: {ro['issue']['warp_instructions_per_launch']/1e6:.0f} M warp instructions per launch = {ro['issue']['frac']:.2f} of the issue slots of 148 SMs × 4 schedulers" if ro.get("issue") else "") +
-  ".  Round 1 → round 2: 308 M → 231 M warp instructions per view in the backward (two-phase kernel), 128 M → 118 M in the forward (cull + compaction before the masks).  "
+  (f" — `roofline.issue`: {rt['render_bwd_warp_instructions_per_view']*8/1e6:.0f} M warp instructions per launch (ncu, this kernel) = {rt['render_bwd_warp_instructions_per_view']*8/ro['issue']['issue_slots']:.2f} of the issue slots of 148 SMs × 4 schedulers "
+   f"(the `roofline.issue` block inside `bench_r02_n1.json` was written with the previous kernel's count, {ro['issue']['warp_instructions_per_launch']/1e6:.0f} M, still in `roofline_traffic.json` at that moment; `bench.py` now ignores counts captured for another kernel variant)" if ro.get("issue") else "") +
+  ".  Round 1 → round 2: 308 M → 231 M warp instructions per view in the backward (two-phase kernel; 186 M with the phase-2 lanes allotted in proportion to work), 128 M → 118 M in the forward (cull + compaction before the masks).  "
   "By the same §8(d) accounting the streaming kernels sit at: K1 0.28, binning (scan + scatter + sorts) 0.90, K8+K9 1.27 of the measured HBM roof "
   "(DESIGN.md §3 table); K1 is latency-bound on its per-tile counting atomics (ncu: long-scoreboard stalls 12 per issue).\n")
 sv = os.path.join(P, "scene_views_r02.log")
 if os.path.isfile(sv):
     w("## One scene-step of the renderer: 8 target views of one Gaussian set + loss + backward, 512×512 (`tools/bench_scene_views.py`)\n")
-    w("The loop of `lightning/network.py:486-495`, the cat of `:525`, the `loss.py` terms (MSE + 1000·distortion + 0.2·normal consistency), `loss.backward()`:\n")
+    w("The loop of `lightning/network.py:486-495`, the cat of `:525`, the `loss.py` terms (MSE + 1000·distortion + 0.2·normal consistency), `loss.backward()` (measured with blend-backward variant 7; the final default shortens every candidate row by a further ~0.44 ms per scene-step at 131 072 Gaussians):\n")
     w("```")
     for line in open(sv):
         if line.startswith("P="):
