@@ -33,7 +33,7 @@ w("| `launches_bench_r02.csv`, `launch_shares_r02.json` | `ncu --metrics gpu__ti
 w("| `roofline_traffic.json` | DRAM bytes and warp instructions per view of the dominant kernel (from the batched capture); `bench.py` reports them as `roofline.traffic` / `roofline.issue` |")
 w("| `sass_histogram_r02.md` | per-kernel SASS opcode histogram of the built library (`tools/sass_histogram.py`): sm_100a cubins, `FFMA2/FMUL2/FADD2`, `REDG.E.ADD.F32x4`, `LDG.E.128`; no spills except 12 bytes in the default blend backward (96 registers for five CTAs per SM; stored and reloaded once per 128-splat round, outside the pair loops) |")
 w("| `parity_sweep_r02.log` | `python tools/parity_sweep.py 7 250` on the kernels as of the scaling runs (blend-backward variant 7): 250 random configurations (500–300k Gaussians, 64–768 px incl. ragged sizes, SH 0–3, needles, saturated scenes, cameras inside the cloud) — **250/250 bit-exact** on every integer state array, colour and aux maps; worst gradient relative error 2.2e-5 |")
-w("| `sanitizer_r02.txt` | compute-sanitizer racecheck / memcheck / synccheck on the final kernels (parity, batched-views, loss, decoder-layout tests): 0 hazards, 0 errors |")
+w("| `sanitizer_r02.txt` | compute-sanitizer racecheck / memcheck / synccheck (parity, batched-views, loss, decoder-layout tests): 0 hazards, 0 errors — run before the last blend-backward change (variant 7); variant 18 keeps the same two `__syncwarp()` points around the X tile and was not re-run under the sanitizer (GPU budget) |")
 w("| `allreduce_probe_n8.log` | latency of the step's one collective (11.5 MB all-reduce) on 8 GPUs under a few NCCL settings |\n")
 
 w("## Headline (1×B200)\n")
