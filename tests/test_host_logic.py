@@ -165,3 +165,60 @@ def test_render_scene_views_rejects_empty_view_list():
     z = torch.zeros((0, 3))
     with pytest.raises(ValueError):
         render_scene_views(z, z, z, z, z, [])
+
+
+def _cpu_settings(H=64, W=48, fov=0.5, deg=1, seed=0, **kw):
+    from lara_b200 import rasterizer as R
+    g = torch.Generator().manual_seed(seed)
+    d = dict(image_height=H, image_width=W, tanfovx=fov, tanfovy=fov, bg=torch.rand(3, generator=g), scale_modifier=1.0,
+             viewmatrix=torch.rand(4, 4, generator=g), projmatrix=torch.rand(4, 4, generator=g), sh_degree=deg,
+             campos=torch.rand(3, generator=g), prefiltered=False, debug=False)
+    d.update(kw)
+    return R.GaussianRasterizationSettings(**d)
+
+
+def test_camera_records_follow_the_header_layout():
+    """pack_cameras: [V, SRF_CAM_FLOATS] rows = view matrix (row-major as stored) | campos | bg | zero pad, at the
+    offsets include/surfel_rasterizer.h names."""
+    import re
+    from lara_b200 import _lib, rasterizer as R
+    hdr = open(os.path.join(ROOT, "include", "surfel_rasterizer.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"#define (SRF_CAM_[A-Z]+) (\d+)", hdr)}
+    assert (consts["SRF_CAM_FLOATS"], consts["SRF_CAM_VIEW"], consts["SRF_CAM_CAMPOS"], consts["SRF_CAM_BG"]) == \
+        (_lib.CAM_FLOATS, _lib.CAM_VIEW, _lib.CAM_CAMPOS, _lib.CAM_BG)
+    sets = [_cpu_settings(seed=s) for s in range(3)]
+    sets[1] = sets[1]._replace(viewmatrix=sets[1].viewmatrix.t())          # LaRa passes a transposed (non-contiguous) view
+    cams = R.pack_cameras(sets, torch.device("cpu"))
+    assert cams.shape == (3, _lib.CAM_FLOATS) and cams.dtype == torch.float32 and cams.is_contiguous()
+    for v, rs in enumerate(sets):
+        assert torch.equal(cams[v, _lib.CAM_VIEW:_lib.CAM_VIEW + 16], rs.viewmatrix.reshape(16))
+        assert torch.equal(cams[v, _lib.CAM_CAMPOS:_lib.CAM_CAMPOS + 3], rs.campos)
+        assert torch.equal(cams[v, _lib.CAM_BG:_lib.CAM_BG + 3], rs.bg)
+        assert torch.count_nonzero(cams[v, _lib.CAM_BG + 3:]) == 0
+
+
+def test_views_of_a_batched_call_must_share_size_fov_and_degree():
+    from lara_b200.multiview import shared_view_settings
+    a = _cpu_settings()
+    assert shared_view_settings([a, _cpu_settings(seed=1)]) == (64, 48, 0.5, 0.5, 1, False, False)
+    assert shared_view_settings([a, _cpu_settings(seed=1, debug=True)])[-1] is True       # one debug view makes the call eager
+    with pytest.raises(RuntimeError, match="one image size"):
+        shared_view_settings([a, _cpu_settings(H=32)])
+    with pytest.raises(RuntimeError, match="field of view"):
+        shared_view_settings([a, _cpu_settings(fov=0.6)])
+    with pytest.raises(RuntimeError, match="SH degree"):
+        shared_view_settings([a, _cpu_settings(deg=2)])
+
+
+def test_view_workspaces_are_the_single_view_ones_back_to_back():
+    """srf_views_workspace_bytes (host only): V per-view workspaces at a byte stride of the single-view size."""
+    from lara_b200 import _lib
+    lib = _lib.load()
+    P, H, W, cap = 5000, 200, 136, 123456
+    g1, t1, i1, s1 = _lib.sizes(lib, P, H, W)
+    e1, p1 = _lib.binning_sizes(lib, cap)
+    for V in (1, 3, 8):
+        g, t, i, e, pl, s = _lib.views_sizes(lib, V, P, H, W, cap)
+        assert (g, t, i, e, pl) == (V * g1, V * t1, V * i1, V * e1, V * p1)
+        assert s >= s1 and s % 256 == 0
+    assert all(x % 256 == 0 for x in (g1, t1, i1, e1, p1))
