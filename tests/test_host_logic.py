@@ -222,3 +222,26 @@ def test_view_workspaces_are_the_single_view_ones_back_to_back():
         assert (g, t, i, e, pl) == (V * g1, V * t1, V * i1, V * e1, V * p1)
         assert s >= s1 and s % 256 == 0
     assert all(x % 256 == 0 for x in (g1, t1, i1, e1, p1))
+
+
+def test_next_row_entries_validate_before_touching_the_device():
+    """The fused epilogue / loss / decoder-layout entries take raw pointers underneath, so wrong inputs must raise the
+    clear errors the reference's torch ops would (checked on the CPU: the checks come before any launch)."""
+    from lara_b200.decoder_layout import gaussians_from_decoder
+    from lara_b200.epilogue import render_img_epilogue
+    from lara_b200.loss import scene_loss
+    H, W = 8, 12
+    with pytest.raises(RuntimeError, match="rendered_image must be a CUDA tensor"):
+        render_img_epilogue(torch.zeros(3, H, W), torch.zeros(8, H, W), torch.zeros(H, W, 6), torch.eye(4), 0.0, "")
+    with pytest.raises(RuntimeError, match=r"parameters must be \[B, N, K\*C\]"):
+        gaussians_from_decoder(torch.zeros(5, 26), torch.zeros(5, 3), 2, 3, 0.0, 0.0, 0.1)
+    with pytest.raises(RuntimeError, match=r"last dim 27 != K\*\(10\+sh_dim\) = 26"):
+        gaussians_from_decoder(torch.zeros(1, 5, 27), torch.zeros(5, 3), 2, 3, 0.0, 0.0, 0.1)
+    with pytest.raises(RuntimeError, match="group_centers must hold N = 5 voxel centres, got 4"):
+        gaussians_from_decoder(torch.zeros(1, 5, 26), torch.zeros(4, 3), 2, 3, 0.0, 0.0, 0.1)
+    with pytest.raises(RuntimeError, match="parameters must be a float32 CUDA tensor"):
+        gaussians_from_decoder(torch.zeros(1, 5, 26), torch.zeros(5, 3), 2, 3, 0.0, 0.0, 0.1)
+    out = {"image": torch.zeros(2, H, W, 3), "rend_normal": torch.zeros(2, H, W, 3), "depth_normal": torch.zeros(2, H, W, 3),
+           "rend_dist": torch.zeros(2, H, W), "acc_map": torch.zeros(2, H, W)}
+    with pytest.raises(RuntimeError, match="scene_loss: .* must be a contiguous float32 CUDA tensor"):
+        scene_loss(out, torch.zeros(2, H, W, 3), 5000)
