@@ -17,14 +17,17 @@
 //   phase 1  lane = pixel.  Every lane walks ITS OWN hits (per-pixel octagon masks, as the forward does)
 //            back to front, does the sequential part and parks (w, GdA, dL/dz) in shared memory
 //            (3 floats per pair, XOR-swizzled so that both phases are bank-conflict free or nearly so).
-//   phase 2  lane = (splat, 0/1).  The two lanes of a splat take its contributing pixels alternately, rebuild the
-//            pixel-dependent coefficients from the splat's record held in registers, and accumulate the 18 gradient
-//            values in registers -- no cross-lane reduction at all; the two lanes are combined with one shuffle per
-//            value and the totals go out as 4 (5) red.global.add.v4.f32 per (warp, splat).
+//   phase 2  lanes in proportion to work.  The 32 lanes are allotted to the group's splats by their number of contributing
+//            pixels (n_i = ceil(c_i / C) lanes for splat i, C the smallest chunk size for which 32 lanes suffice); every lane
+//            takes a chunk of its splat's pixels, rebuilds the pixel-dependent coefficients from the splat's record held in
+//            registers and accumulates the 18 gradient values in registers -- no cross-lane reduction at all; the partial
+//            sums go out as 4 (5) red.global.add.v4.f32 per lane.  (P2WALK 0..2 are the earlier fixed layouts, two lanes
+//            per splat, kept for A/B.)
 // Phase 1 evaluates pairs with MUFU.RCP / MUFU.EX2 and re-evaluates with the forward's exact sequence only within a
 // narrow band around the forward's decision thresholds (eval_pair_bwd below).
-// What is kept from round 1: CTA per 16x16 tile in LPT order, the list walked back to front from the tile's
-// deepest used entry in staged rounds, warp-level octagon cull, packed fp32x2 arithmetic, MUFU.RCP.
+// What is kept from round 1: tiles in LPT order (the default variant runs one 4-warp CTA per 16x8 half tile, five per
+// SM), the list walked back to front from the tile's deepest used entry in staged rounds, warp-level octagon cull,
+// packed fp32x2 arithmetic, MUFU.RCP.
 #include "surfel_common.cuh"
 #include "surfel_kernels.h"
 
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
 
                 __syncwarp();     // phase-1 stores to the X tile are visible to the whole warp
 
-                // ================= phase 2: lane = (splat i, half block h) =================
+                // ================= phase 2: lane = (splat, chunk of its pixels) =================
                 // valid-pair words: lane i (< 16) receives "which pixels contributed to splat i"
                 const uint32_t tw = transpose32(vbits, lane);
                 int own = p2_i;               // the splat of the group this lane accumulates for
