@@ -403,19 +403,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) render_bwd_kernel(RenderBwdArgs
                     // below makes C trips.  C is the smallest value for which the lanes suffice (sum n_i <= 32;
                     // C = 16 always does): ~8.5 trips per group on the bench scene against ~15 with two lanes per
                     // splat (tools/phase2_balance.py).
-                    const int cnt = __popc(tw);                    // lanes >= 16 hold no word: 0
-                    if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
+                    const int npx = __popc(tw);                    // lanes >= 16 hold no word: 0
+                    if (__ballot_sync(0xffffffffu, npx != 0) == 0u) continue;
                     // lane (C - 1) + 16 h adds up ceil(c_i / C) over the splats 8 h .. 8 h + 7
                     int part = 0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const int c = __shfl_sync(0xffffffffu, cnt, p2_h * 8 + k);
+                        const int c = __shfl_sync(0xffffffffu, npx, p2_h * 8 + k);
                         part += (int)(((uint32_t)(c + p2_i) * candM) >> 16);
                     }
                     const int lanes_needed = part + __shfl_xor_sync(0xffffffffu, part, 16);
                     const int C = __ffs(__ballot_sync(0xffffffffu, lanes_needed <= 32) & 0xffffu);      // 1..16
                     const uint32_t M = __shfl_sync(0xffffffffu, candM, C - 1);
-                    const int n_mine = (int)(((uint32_t)(cnt + C - 1) * M) >> 16);                       // lanes >= 16: 0
+                    const int n_mine = (int)(((uint32_t)(npx + C - 1) * M) >> 16);                       // lanes >= 16: 0
                     int end = n_mine;                              // inclusive scan over the lanes 0..15
 #pragma unroll
                     for (int o = 1; o < kBwdGroup; o <<= 1) {
