@@ -599,24 +599,28 @@ cudaError_t launch_render_bwd(const RenderBwdArgs& a, cudaStream_t stream) {
     if (variant == 1) return launch_render_bwd_v1(a, stream);
     prof_start(K_RENDER_BWD, stream);
     cudaError_t e = cudaSuccess;
+    // <splats per round, warps per CTA, CTAs per SM, exact pair evaluation, phase-2 walk, upstream gradients from smem,
+    //  list-entry prefetch, explicit shared addressing in phase 1, pixel centre pinned in registers>
+    // us per view at the north-star point in profiles/bwd_variants_r02.log; 2..8 are the fixed phase-2 layouts of the
+    // first two-phase kernel (7 was its default), 9..17 the steps from there to the default.
     switch (variant) {
-        case 3: e = launch_variant<160, 8, 3, false, 1, true>(a, stream); break;
-        case 4: e = launch_variant<256, 8, 2, false, 0, false>(a, stream); break;
-        case 5: e = launch_variant<256, 8, 2, true, 1, false>(a, stream); break;
-        case 6: e = launch_variant<256, 4, 4, false, 1, false>(a, stream); break;      // half-tile CTAs
         case 2: e = launch_variant<256, 8, 2, false, 1, false>(a, stream); break;      // one CTA per tile, own-half phase-2 lanes
+        case 3: e = launch_variant<160, 8, 3, false, 1, true>(a, stream); break;       // three CTAs per SM
+        case 4: e = launch_variant<256, 8, 2, false, 0, false>(a, stream); break;      // lock-step phase 2
+        case 5: e = launch_variant<256, 8, 2, true, 1, false>(a, stream); break;       // exact pair evaluation everywhere
+        case 6: e = launch_variant<256, 4, 4, false, 1, false>(a, stream); break;      // half-tile CTAs
+        case 7: e = launch_variant<256, 4, 4, false, 2, false>(a, stream); break;      // half-tile CTAs, shared phase-2 lanes (318 us)
         case 8: e = launch_variant<256, 8, 2, false, 2, false>(a, stream); break;      // one CTA per tile, shared phase-2 lanes
-        case 9: e = launch_variant<256, 4, 4, false, 3, false>(a, stream); break;      // half-tile CTAs, phase-2 lanes in proportion to work
-        case 10: e = launch_variant<256, 8, 2, false, 3, false>(a, stream); break;     // one CTA per tile, the same
-        case 11: e = launch_variant<128, 4, 5, false, 3, true>(a, stream); break;      // five half-tile CTAs per SM (<= 102 registers)
-        case 12: e = launch_variant<128, 4, 5, false, 3, false>(a, stream); break;
-        case 13: e = launch_variant<64, 4, 6, false, 3, true>(a, stream); break;
-        case 14: e = launch_variant<128, 8, 3, false, 3, true>(a, stream); break;
-        case 15: e = launch_variant<128, 4, 5, false, 2, false>(a, stream); break;
-        case 16: e = launch_variant<128, 4, 5, false, 3, false, true>(a, stream); break;
-        case 17: e = launch_variant<128, 4, 5, false, 3, false, true, true>(a, stream); break;
-        case 18: e = launch_variant<128, 4, 5, false, 3, false, true, true, true>(a, stream); break;
-        default: e = launch_variant<256, 4, 4, false, 2, false>(a, stream); break;     // 7: half-tile CTAs, shared phase-2 lanes
+        case 9: e = launch_variant<256, 4, 4, false, 3, false>(a, stream); break;      // 7 + phase-2 lanes in proportion to work (274 us)
+        case 10: e = launch_variant<256, 8, 2, false, 3, false>(a, stream); break;     // the same, one CTA per tile
+        case 11: e = launch_variant<128, 4, 5, false, 3, true>(a, stream); break;      // five half-tile CTAs per SM, upstream grads from smem
+        case 12: e = launch_variant<128, 4, 5, false, 3, false>(a, stream); break;     // five half-tile CTAs per SM (267 us)
+        case 13: e = launch_variant<64, 4, 6, false, 3, true>(a, stream); break;       // six CTAs per SM, 64-splat rounds
+        case 14: e = launch_variant<128, 8, 3, false, 3, true>(a, stream); break;      // six CTAs' worth of warps as three 8-warp CTAs
+        case 15: e = launch_variant<128, 4, 5, false, 2, false>(a, stream); break;     // five CTAs per SM WITHOUT the allotment (325 us)
+        case 16: e = launch_variant<128, 4, 5, false, 3, false, true>(a, stream); break;        // 12 + prefetch
+        case 17: e = launch_variant<128, 4, 5, false, 3, false, true, true>(a, stream); break;  // 16 + explicit shared addressing
+        default: e = launch_variant<128, 4, 5, false, 3, false, true, true, true>(a, stream); break;   // 18: 17 + pinned pixel centre (262 us)
     }
     prof_stop(K_RENDER_BWD, stream);
     return e != cudaSuccess ? e : cudaGetLastError();
