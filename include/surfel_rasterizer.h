@@ -261,7 +261,7 @@ int srf_profile_begin(void);
 int srf_profile_end(float* ms_out, int* launches_out, int n);
 /* A/B selection of the blend-backward kernel variant for tools/ (same meaning as the SRF_BWD_VARIANT
  * environment variable, which is read once); returns the variant that was selected before.
- * Every variant computes the same gradients; lara_b200/csrc/render_bwd.cu lists them. */
+ * The variants differ in work decomposition, not in arithmetic; lara_b200/csrc/render_bwd.cu lists them. */
 int srf_select_bwd_variant(int variant);
 
 /* ---- markVisible (DSR/rasterize_points.cu:242-261, rasterizer_impl.cu:141-153) ----
